@@ -1,0 +1,153 @@
+"""CPU tests that pin the oracle (no GPU).
+
+Stage 1 is pinned to the unmodified reference through tests/golden/ns_*.npz (pyNNGP/nngp.py:49-62 run
+by tests/golden/make_golden.py).  Stages 2-3 are unpinned by the reference (nngp.py:73-96 are stubs)
+and are anchored to the dense-GP identity and closed-form hand cases.
+"""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+from oracle import nngp_oracle as orc
+from pynngp_b200.synthetic import synthetic
+
+TIE_FREE = ["test_init_shape", "cfg1", "d2_m15", "d3_m30", "d1_m5", "d3_m32"]
+
+
+@pytest.mark.parametrize("name", TIE_FREE)
+def test_knn_c_oracle_matches_reference_golden(golden_dir, name):
+    g = np.load(os.path.join(golden_dir, f"ns_{name}.npz"))
+    tab = orc.c_knn_ordered(g["coords"], int(g["m"]))
+    assert tab.dtype == np.int32
+    assert np.array_equal(tab, g["Ns"])  # bit-exact, order included
+
+
+@pytest.mark.parametrize("name", ["test_init_shape", "d1_m5", "d3_m32"])
+def test_knn_numpy_oracle_matches_reference_golden(golden_dir, name):
+    g = np.load(os.path.join(golden_dir, f"ns_{name}.npz"))
+    Ns = orc.np_knn_ordered(g["coords"], int(g["m"]))
+    assert Ns[0] == []
+    assert np.array_equal(orc.ns_to_table(Ns, int(g["m"])), g["Ns"])
+
+
+def test_knn_lattice_ties_distance_multiset(golden_dir):
+    """On tied inputs the reference's KD-tree order is unspecified: the oracle's
+    (d2, j) rule must give the same multiset of neighbour distances per row."""
+    g = np.load(os.path.join(golden_dir, "ns_lattice.npz"))
+    s, ref = g["coords"], g["Ns"]
+    tab = orc.c_knn_ordered(s, int(g["m"]))
+    for i in range(len(s)):
+        a, b = tab[i][tab[i] >= 0], ref[i][ref[i] >= 0]
+        assert len(a) == len(b)
+        da = np.sort(orc.np_dist2(s[i], s[a])) if len(a) else np.zeros(0)
+        db = np.sort(orc.np_dist2(s[i], s[b])) if len(b) else np.zeros(0)
+        assert np.array_equal(da, db)
+        # ascending (d2, j) inside the oracle's own rows
+        if len(a) > 1:
+            d = orc.np_dist2(s[i], s[a])
+            assert all((d[k], a[k]) < (d[k + 1], a[k + 1]) for k in range(len(a) - 1))
+
+
+def test_knn_duplicates_ties_by_index():
+    s = np.array([[0.5, 0.5]] * 6 + [[0.25, 0.5]] * 3, dtype=np.float64)
+    tab = orc.c_knn_ordered(s, 4)
+    assert tab[0].tolist() == [-1, -1, -1, -1]
+    assert tab[3].tolist() == [0, 1, 2, -1]
+    assert tab[5].tolist() == [0, 1, 2, 3]
+    assert tab[8].tolist() == [6, 7, 0, 1]
+    assert np.array_equal(tab, orc.ns_to_table(orc.np_knn_ordered(s, 4), 4))
+
+
+def test_knn_threads_and_ranges():
+    s, _ = synthetic(700, 3, 5)
+    full = orc.c_knn_ordered(s, 7)
+    assert np.array_equal(full, orc.c_knn_ordered(s, 7, threads=4))
+    part = orc.c_knn_ordered(s, 7, lo=100, hi=300)
+    assert np.array_equal(part[100:300], full[100:300])
+    assert (part[:100] == -1).all() and (part[300:] == -1).all()
+
+
+@pytest.mark.parametrize("kernel_id", [0, 1, 2])
+@pytest.mark.parametrize("D", [1, 2, 3])
+def test_c_matches_numpy_per_location(kernel_id, D):
+    s, y = synthetic(120, D, 40 + D)
+    m = 9
+    nbr = orc.c_knn_ordered(s, m)
+    eps2 = np.linspace(0.0, 0.02, len(s))
+    sig, phi, tau = 1.3, 5.0, 0.07
+    npo = orc.NumpyNNGP(s, y, nbr, kernel_id, sig, phi, tau, eps2)
+    CN, cc, cs = orc.c_cov_blocks(s, nbr, kernel_id, sig, phi, tau, eps2)
+    B, F = orc.c_factors(s, y, nbr, kernel_id, sig, phi, tau, eps2)
+    for i in [0, 1, 2, 5, 8, 9, 10, 57, 119]:
+        p = min(i, m)
+        np.testing.assert_allclose(CN[i, :p, :p], npo._CNs(i), rtol=1e-14)
+        np.testing.assert_allclose(cc[i, :p], npo._Ccross(i), rtol=1e-14)
+        assert cs[i] == npo._Cs(i)
+        np.testing.assert_allclose(B[i, :p], npo._Bsi(i), rtol=1e-10, atol=1e-13)
+        assert (B[i, p:] == 0).all()
+        np.testing.assert_allclose(F[i], npo._Fsi(i), rtol=1e-12)
+    slog, squad, bad = orc.c_loglik(s, y, nbr, kernel_id, sig, phi, tau, eps2)
+    s2, q2 = npo.loglik_terms()
+    assert bad == 0
+    np.testing.assert_allclose([slog, squad], [s2, q2], rtol=1e-12)
+    # threaded split == single pass (summation order only)
+    t = orc.c_loglik(s, y, nbr, kernel_id, sig, phi, tau, eps2, threads=3)
+    np.testing.assert_allclose(t[:2], [slog, squad], rtol=1e-13)
+
+
+@pytest.mark.parametrize("kernel_id", [0, 1, 2])
+def test_dense_gp_identity(kernel_id):
+    """Known answer: with m = n-1 every location conditions on all predecessors and the NNGP density
+    is the exact N(0, sigma2 rho + tau2 I) density."""
+    n = 60  # ORACLE_MAX_M = 64 bounds m
+    s, y = synthetic(n, 2, 77)
+    nbr = orc.c_knn_ordered(s, n - 1)
+    sig, phi, tau = 1.0, 6.0, 0.1
+    slog, squad, bad = orc.c_loglik(s, y, nbr, kernel_id, sig, phi, tau)
+    assert bad == 0
+    ll = orc.loglik_from_terms(slog, squad, n)
+    exact = orc.dense_gp_loglik(s, y, kernel_id, sig, phi, tau)
+    assert abs(ll - exact) <= 1e-12 * abs(exact)
+
+
+def test_dense_gp_identity_numpy_larger():
+    n = 150
+    s, y = synthetic(n, 3, 78)
+    Ns = orc.np_knn_ordered(s, n - 1)
+    nbr = orc.ns_to_table(Ns, n - 1)
+    npo = orc.NumpyNNGP(s, y, nbr, 1, 0.8, 4.0, 0.2)
+    slog, squad = npo.loglik_terms()
+    exact = orc.dense_gp_loglik(s, y, 1, 0.8, 4.0, 0.2)
+    assert abs(orc.loglik_from_terms(slog, squad, n) - exact) <= 1e-11 * abs(exact)
+
+
+def test_hand_cases():
+    s = np.array([[0.0, 0.0], [0.3, 0.4]])  # distance 0.5
+    y = np.array([1.5, -0.5])
+    nbr = np.array([[-1], [0]], dtype=np.int32)
+    sig, phi, tau = 2.0, 3.0, 0.5
+    B, F = orc.c_factors(s, y, nbr, 0, sig, phi, tau)
+    # i = 0: no neighbours -> F = C_ii
+    assert B[0, 0] == 0.0 and F[0] == sig + tau
+    # p = 1: b = sigma2 rho(d) / (sigma2 + tau2)
+    rho = np.exp(-phi * 0.5)
+    np.testing.assert_allclose(B[1, 0], sig * rho / (sig + tau), rtol=1e-15)
+    np.testing.assert_allclose(F[1], sig + tau - (sig * rho) ** 2 / (sig + tau), rtol=1e-15)
+    slog, squad, bad = orc.c_loglik(s, y, nbr, 0, sig, phi, tau)
+    r1 = y[1] - B[1, 0] * y[0]
+    np.testing.assert_allclose(slog, np.log(F[0]) + np.log(F[1]), rtol=1e-15)
+    np.testing.assert_allclose(squad, y[0] ** 2 / F[0] + r1 ** 2 / F[1], rtol=1e-15)
+
+
+def test_non_spd_is_counted_not_nan():
+    s = np.array([[0.0, 0.0], [0.0, 0.0], [0.0, 0.0], [1.0, 1.0]])  # duplicates, no nugget
+    y = np.ones(4)
+    nbr = orc.c_knn_ordered(s, 3)
+    slog, squad, bad = orc.c_loglik(s, y, nbr, 0, 1.0, 1.0, 0.0)
+    assert bad >= 1 and np.isfinite(slog) and np.isfinite(squad)
+
+
+def test_golden_files_present(golden_dir):
+    assert len(glob.glob(os.path.join(golden_dir, "ns_*.npz"))) >= 7
