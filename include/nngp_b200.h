@@ -1,0 +1,117 @@
+/*
+ * nngp_b200.h -- C ABI of libnngp_b200.so: the B200 (sm_100a) NNGP likelihood hot path.
+ *
+ * The reference (bwpriest/pyNNGP) is a pure-Python class with no FFI of its own; each entry point
+ * below names the reference symbol (pyNNGP/nngp.py:LINE) whose work it takes over, and
+ * INTEGRATION.md shows the ctypes stub a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - every function returns 0 on success and a nonzero NNGP_E* code on failure; the message is
+ *     available from nngp_last_error(h) (or nngp_last_error(NULL) for a failed nngp_create).
+ *   - one handle = one CUDA device = one shard of the ordering (rows [lo, hi) of the location
+ *     list).  Multi-GPU runs use one process (and one handle) per GPU; the cross-GPU sum of the
+ *     3*K partial statistics is the caller's allreduce (NCCL through torch.distributed in
+ *     pynngp_b200/dist.py).
+ *   - the caller owns every host buffer; the library copies in / out and never keeps host
+ *     pointers.  The handle owns device memory and its stream.
+ *   - plain-pointer calls are synchronous on return.  *_device calls take device pointers and a
+ *     cudaStream_t (as void*), are asynchronous, and are what an on-device sweep/MCMC loop uses.
+ *   - a handle is not thread-safe; distinct handles are independent.
+ *   - there is NO CPU fallback: without a CUDA device nngp_create fails with NNGP_ENODEVICE.
+ */
+#ifndef NNGP_B200_H
+#define NNGP_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct nngp_handle nngp_handle;
+
+enum {
+    NNGP_OK = 0,
+    NNGP_EINVAL = 1,    /* bad argument (NULL, m out of range, D unsupported, ...) */
+    NNGP_ENODEVICE = 2, /* no CUDA device / wrong architecture */
+    NNGP_ECUDA = 3,     /* a CUDA runtime call failed; see nngp_last_error */
+    NNGP_ESTATE = 4     /* call order: data / neighbours not set yet */
+};
+
+enum { NNGP_F64 = 0, NNGP_F32 = 1 };                               /* arithmetic of stages 2-3 */
+enum { NNGP_EXPONENTIAL = 0, NNGP_MATERN32 = 1, NNGP_MATERN52 = 2 }; /* kernel_id */
+
+#define NNGP_MAX_M 32   /* neighbours per location (north_star: m <= 32) */
+#define NNGP_MAX_D 3    /* spatial dimension of the coordinates */
+#define NNGP_NPARAM 4   /* one parameter vector = {sigma2, phi, tau2, nu(reserved)} */
+#define NNGP_NSTAT 3    /* one result = {sum log F_i, sum r_i^2/F_i, n_bad} */
+
+/* Library / device -------------------------------------------------------------------------- */
+const char *nngp_version(void);
+const char *nngp_last_error(const nngp_handle *h);
+
+/* Creates an engine on CUDA device `device` computing stages 2-3 in `dtype` (NNGP_F64|NNGP_F32;
+ * stage 1 is always fp64).  Replaces: object construction, nngp.py:6-12. */
+int nngp_create(nngp_handle **h, int device, int dtype);
+void nngp_destroy(nngp_handle *h);
+
+/* Uploads the reference set and the response.  coords: n x D row-major fp64 (the reference's
+ * `s`, nngp.py:29-31 'S=T' branch: s = t); y: n fp64 (nngp.py:8); eps2: n fp64 per-observation
+ * variances added to the diagonal (the square of nngp.py:9's `eps`), or NULL.
+ * Resets the shard to [0, n) and drops any neighbour table. */
+int nngp_set_data(nngp_handle *h, const double *coords, int64_t n, int D, const double *y,
+                  const double *eps2);
+/* Replaces y only (n fp64), keeping coordinates and neighbours. */
+int nngp_set_y(nngp_handle *h, const double *y);
+
+/* Rows [lo, hi) of the ordering are this handle's shard: stages 2-3 and the returned partial
+ * statistics cover exactly these rows.  Coordinates / y stay replicated in full. */
+int nngp_set_shard(nngp_handle *h, int64_t lo, int64_t hi);
+
+/* Stage 1 -- ordered k-NN.  Replaces _make_s_neighbor_sets, nngp.py:49-62: for each i the
+ * min(m, i) nearest j < i in ascending (d2, j), d2 the sklearn fp64 squared distance; row i of the
+ * device table (n x m int32, -1 padded) is filled.  Query tiles (NNGP_KNN_TILE consecutive rows)
+ * are taken heaviest first; with tile_stride > 1 only tiles whose rank from the heavy end is
+ * congruent to tile_offset are computed (balanced multi-GPU split) and every other row is set to
+ * NNGP_ROW_UNSET so an elementwise MAX across ranks assembles the table. */
+#define NNGP_KNN_TILE 128
+#define NNGP_ROW_UNSET (-2)
+int nngp_build_neighbors(nngp_handle *h, int m, int tile_offset, int tile_stride);
+/* Injects a table (n x m int32 row-major, -1 padded; valid entries first in each row). */
+int nngp_set_neighbors(nngp_handle *h, const int32_t *idx, int m);
+int nngp_get_neighbors(nngp_handle *h, int32_t *out);
+/* Device address of the n x m int32 table (for an NCCL exchange by the caller), or NULL. */
+void *nngp_neighbors_device_ptr(nngp_handle *h);
+
+/* Stages 2-3 fused -- the metric's call.  For each of K parameter vectors
+ * (params: K x NNGP_NPARAM fp64) builds C_N(i), c_i, C(i,i) (_CNs nngp.py:78-82, _Ccross
+ * nngp.py:84-86, _Cs nngp.py:92-96), factorises (_Bsi nngp.py:73-76, _Fsi nngp.py:88-90) and
+ * reduces over the shard.  out: K x NNGP_NSTAT fp64 = {sum log F_i, sum (y_i - b_i^T y_N(i))^2/F_i,
+ * n_bad}; locations whose factorisation met a non-positive pivot are counted in n_bad and left out
+ * of the sums. */
+int nngp_loglik(nngp_handle *h, int kernel_id, const double *params, int K, double *out);
+/* Same with device pointers on `stream` (NULL = the handle's stream); no host synchronisation. */
+int nngp_loglik_device(nngp_handle *h, int kernel_id, const double *d_params, int K,
+                       double *d_out, void *stream);
+
+/* Per-location factors for rows [i0, i1) (any rows, not only the shard): B (i1-i0) x m fp64
+ * (b_i = C_N(i)^-1 c_i, zero padded; _Bsi nngp.py:73-76), F (i1-i0) (_Fsi nngp.py:88-90).
+ * Either output may be NULL. */
+int nngp_factors(nngp_handle *h, int kernel_id, const double *params, int64_t i0, int64_t i1,
+                 double *B, double *F);
+/* Covariance blocks for rows [i0, i1): CN (i1-i0) x m x m (zero outside the leading p x p; _CNs
+ * nngp.py:78-82), cc (i1-i0) x m (_Ccross nngp.py:84-86), cs (i1-i0) (_Cs nngp.py:92-96).  Any
+ * output may be NULL. */
+int nngp_cov_blocks(nngp_handle *h, int kernel_id, const double *params, int64_t i0, int64_t i1,
+                    double *CN, double *cc, double *cs);
+
+/* Introspection for the bench: number of kernels this handle has launched so far, and a measured
+ * FP64 (dtype NNGP_F64) or FP32 FMA peak of the device in thread-instructions per second
+ * (register-resident dependent-chain microbenchmark, `iters` FMAs per thread). */
+int64_t nngp_launch_count(const nngp_handle *h);
+int nngp_measure_fma_peak(nngp_handle *h, int dtype, int iters, double *instr_per_s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NNGP_B200_H */

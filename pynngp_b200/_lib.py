@@ -1,0 +1,199 @@
+"""ctypes binding of libnngp_b200.so (C ABI: include/nngp_b200.h).
+
+There is no CPU fallback: if the shared library is missing or no B200 is present, loading /
+engine creation raises.  Build with ``python -m pynngp_b200.build``.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+import numpy as np
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "_C", "libnngp_b200.so")
+
+F64, F32 = 0, 1
+NPARAM, NSTAT = 4, 3
+MAX_M, MAX_D = 32, 3
+KNN_TILE = 128
+ROW_UNSET = -2
+
+_c_double_p = ctypes.POINTER(ctypes.c_double)
+_c_int32_p = ctypes.POINTER(ctypes.c_int32)
+_handle_p = ctypes.c_void_p
+
+# name -> (restype, argtypes); every symbol include/nngp_b200.h declares
+SIGNATURES = {
+    "nngp_version": (ctypes.c_char_p, []),
+    "nngp_last_error": (ctypes.c_char_p, [_handle_p]),
+    "nngp_create": (ctypes.c_int, [ctypes.POINTER(_handle_p), ctypes.c_int, ctypes.c_int]),
+    "nngp_destroy": (None, [_handle_p]),
+    "nngp_set_data": (ctypes.c_int, [_handle_p, _c_double_p, ctypes.c_int64, ctypes.c_int, _c_double_p, _c_double_p]),
+    "nngp_set_y": (ctypes.c_int, [_handle_p, _c_double_p]),
+    "nngp_set_shard": (ctypes.c_int, [_handle_p, ctypes.c_int64, ctypes.c_int64]),
+    "nngp_build_neighbors": (ctypes.c_int, [_handle_p, ctypes.c_int, ctypes.c_int, ctypes.c_int]),
+    "nngp_set_neighbors": (ctypes.c_int, [_handle_p, _c_int32_p, ctypes.c_int]),
+    "nngp_get_neighbors": (ctypes.c_int, [_handle_p, _c_int32_p]),
+    "nngp_neighbors_device_ptr": (ctypes.c_void_p, [_handle_p]),
+    "nngp_loglik": (ctypes.c_int, [_handle_p, ctypes.c_int, _c_double_p, ctypes.c_int, _c_double_p]),
+    "nngp_loglik_device": (ctypes.c_int, [_handle_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]),
+    "nngp_factors": (ctypes.c_int, [_handle_p, ctypes.c_int, _c_double_p, ctypes.c_int64, ctypes.c_int64, _c_double_p, _c_double_p]),
+    "nngp_cov_blocks": (ctypes.c_int, [_handle_p, ctypes.c_int, _c_double_p, ctypes.c_int64, ctypes.c_int64, _c_double_p, _c_double_p, _c_double_p]),
+    "nngp_launch_count": (ctypes.c_int64, [_handle_p]),
+    "nngp_measure_fma_peak": (ctypes.c_int, [_handle_p, ctypes.c_int, ctypes.c_int, _c_double_p]),
+}
+
+_lib = None
+
+
+class NNGPError(RuntimeError):
+    """A libnngp_b200 call returned a nonzero status."""
+
+
+def load():
+    """dlopen the in-tree library and bind every symbol; raises if it is not built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise NNGPError(
+                f"{LIB_PATH} is missing: build it with `python -m pynngp_b200.build` "
+                "(pynngp_b200 has no CPU fallback)")
+        lib = ctypes.CDLL(LIB_PATH)
+        for name, (restype, argtypes) in SIGNATURES.items():
+            fn = getattr(lib, name)  # AttributeError if the .so does not export it
+            fn.restype = restype
+            fn.argtypes = argtypes
+        _lib = lib
+    return _lib
+
+
+def _dp(a):
+    return None if a is None else a.ctypes.data_as(_c_double_p)
+
+
+def _f64(a, shape=None):
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    if shape is not None and a.shape != shape:
+        raise ValueError(f"expected shape {shape}, got {a.shape}")
+    return a
+
+
+class Engine:
+    """One handle = one GPU = one shard of the ordering.  Thin, 1:1 over the C ABI."""
+
+    def __init__(self, device=0, dtype="float64"):
+        self._lib = load()
+        self._h = _handle_p()
+        code = {"float64": F64, "float32": F32}.get(str(dtype))
+        if code is None:
+            raise ValueError("dtype must be 'float64' or 'float32'")
+        rc = self._lib.nngp_create(ctypes.byref(self._h), int(device), code)
+        if rc != 0:
+            msg = self._lib.nngp_last_error(None).decode()
+            self._h = None
+            raise NNGPError(f"nngp_create failed ({rc}): {msg}")
+        self.device, self.dtype = int(device), str(dtype)
+        self.n = self.D = self.m = 0
+
+    def _check(self, rc, what):
+        if rc != 0:
+            raise NNGPError(f"{what} failed ({rc}): {self._lib.nngp_last_error(self._h).decode()}")
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.nngp_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- data ------------------------------------------------------------------------------------
+    def set_data(self, coords, y, eps2=None):
+        coords = _f64(coords)
+        if coords.ndim != 2:
+            raise ValueError("coords must be (n, D)")
+        n, D = coords.shape
+        y = _f64(y, (n,))
+        eps2 = None if eps2 is None else _f64(eps2, (n,))
+        self._check(self._lib.nngp_set_data(self._h, _dp(coords), n, D, _dp(y), _dp(eps2)), "nngp_set_data")
+        self.n, self.D, self.m = n, D, 0
+
+    def set_y(self, y):
+        y = _f64(y, (self.n,))
+        self._check(self._lib.nngp_set_y(self._h, _dp(y)), "nngp_set_y")
+
+    def set_shard(self, lo, hi):
+        self._check(self._lib.nngp_set_shard(self._h, int(lo), int(hi)), "nngp_set_shard")
+
+    # -- stage 1 ---------------------------------------------------------------------------------
+    def build_neighbors(self, m, tile_offset=0, tile_stride=1):
+        self._check(self._lib.nngp_build_neighbors(self._h, int(m), int(tile_offset), int(tile_stride)),
+                    "nngp_build_neighbors")
+        self.m = int(m)
+
+    def set_neighbors(self, table):
+        table = np.ascontiguousarray(table, dtype=np.int32)
+        if table.ndim != 2 or table.shape[0] != self.n:
+            raise ValueError("neighbour table must be (n, m) int32")
+        self._check(self._lib.nngp_set_neighbors(self._h, table.ctypes.data_as(_c_int32_p), table.shape[1]),
+                    "nngp_set_neighbors")
+        self.m = table.shape[1]
+
+    def get_neighbors(self):
+        out = np.empty((self.n, self.m), dtype=np.int32)
+        self._check(self._lib.nngp_get_neighbors(self._h, out.ctypes.data_as(_c_int32_p)), "nngp_get_neighbors")
+        return out
+
+    def neighbors_device_ptr(self):
+        return self._lib.nngp_neighbors_device_ptr(self._h)
+
+    # -- stages 2-3 --------------------------------------------------------------------------------
+    def loglik(self, kernel_id, params):
+        """params (K, 4) -> stats (K, 3) = [sum log F, sum r^2/F, n_bad] over the shard."""
+        params = _f64(params)
+        if params.ndim == 1:
+            params = params[None, :]
+        if params.shape[1] != NPARAM:
+            raise ValueError("params must be (K, 4): sigma2, phi, tau2, nu")
+        out = np.empty((params.shape[0], NSTAT), dtype=np.float64)
+        self._check(self._lib.nngp_loglik(self._h, int(kernel_id), _dp(params), params.shape[0], _dp(out)),
+                    "nngp_loglik")
+        return out
+
+    def loglik_device(self, kernel_id, d_params, K, d_out, stream=None):
+        self._check(self._lib.nngp_loglik_device(self._h, int(kernel_id), ctypes.c_void_p(d_params), int(K),
+                                                 ctypes.c_void_p(d_out), ctypes.c_void_p(stream or 0)),
+                    "nngp_loglik_device")
+
+    def factors(self, kernel_id, params, i0=0, i1=None, want_B=True, want_F=True):
+        i1 = self.n if i1 is None else i1
+        params = _f64(params, (NPARAM,))
+        B = np.empty((i1 - i0, self.m), dtype=np.float64) if want_B else None
+        F = np.empty(i1 - i0, dtype=np.float64) if want_F else None
+        self._check(self._lib.nngp_factors(self._h, int(kernel_id), _dp(params), i0, i1, _dp(B), _dp(F)),
+                    "nngp_factors")
+        return B, F
+
+    def cov_blocks(self, kernel_id, params, i0=0, i1=None):
+        i1 = self.n if i1 is None else i1
+        params = _f64(params, (NPARAM,))
+        CN = np.empty((i1 - i0, self.m, self.m), dtype=np.float64)
+        cc = np.empty((i1 - i0, self.m), dtype=np.float64)
+        cs = np.empty(i1 - i0, dtype=np.float64)
+        self._check(self._lib.nngp_cov_blocks(self._h, int(kernel_id), _dp(params), i0, i1, _dp(CN), _dp(cc), _dp(cs)),
+                    "nngp_cov_blocks")
+        return CN, cc, cs
+
+    # -- introspection -----------------------------------------------------------------------------
+    def launch_count(self):
+        return int(self._lib.nngp_launch_count(self._h))
+
+    def measure_fma_peak(self, dtype="float64", iters=4096):
+        v = ctypes.c_double(0.0)
+        self._check(self._lib.nngp_measure_fma_peak(self._h, F64 if dtype == "float64" else F32, int(iters),
+                                                    ctypes.byref(v)), "nngp_measure_fma_peak")
+        return v.value

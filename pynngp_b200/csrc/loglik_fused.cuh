@@ -1,0 +1,476 @@
+// loglik_fused.cuh -- stages 2+3 of the NNGP hot path as ONE kernel (sm_100a).
+//
+// Takes over the reference's per-location accessors (all stubs upstream):
+//   _CNs nngp.py:78-82, _Ccross nngp.py:84-86, _Cs nngp.py:92-96  -> covariance build
+//   _Bsi nngp.py:73-76, _Fsi nngp.py:88-90                         -> factorisation
+//   and the reduction BASELINE.json north_star defines: sum_i [log F_i + r_i^2 / F_i].
+//
+// Mapping.  A location i with p <= m neighbours is the P x P augmented SPD matrix
+//     M = [[C_N(i), c_i], [c_i^T, C(i,i)]],   rows 0..p-1 = neighbours (table order), rows p..P-2 =
+//     identity padding, row P-1 = the location itself,
+// with the right-hand side w = [y_N(i); 0; y_i].  An LDL^T elimination of M gives, at the last
+// pivot, D_{P-1} = F_i and the eliminated w_{P-1} = r_i = y_i - b_i^T y_N(i): the log-likelihood
+// needs no back-substitution.  G lanes share one location (P = G*R rows, lane q owns rows
+// q, q+G, ..., kept in registers); a warp carries 32/G locations.  Pivot column entries travel by
+// width-G warp shuffles, everything else is lane-local FP64 (or FP32) arithmetic.  Neighbour
+// coordinates are gathered once per location as 32-byte records and staged in shared memory for
+// the column reads of the covariance build.  Block partials are written per block and summed in a
+// fixed order by the last block to finish (deterministic for a given grid).
+//
+// Bound: the FP64 (FP32) vector pipe -- each pair costs a sqrt and an exp; HBM traffic is the
+// 4m+32 B/location of compulsory reads.  Tensor cores do not apply: per-location work is
+// a 16x16 / 32x32 factorisation with a serial pivot chain plus transcendental covariance entries.
+#pragma once
+#include <math.h>
+
+#include "nngp_common.cuh"
+
+namespace nngp_fused {
+
+constexpr int kThreads = 128;
+constexpr int kWarps = kThreads / 32;
+
+template <typename T, bool DIM3>
+struct StagePt;
+template <typename T>
+struct __align__(2 * sizeof(T)) StagePt<T, false> {
+    T x, y;
+};
+template <typename T>
+struct __align__(16) StagePt<T, true> {
+    T x, y, z, pad;
+};
+
+__device__ __forceinline__ double t_fma(double a, double b, double c) { return fma(a, b, c); }
+__device__ __forceinline__ float t_fma(float a, float b, float c) { return fmaf(a, b, c); }
+
+// ---- branch-free math for the covariance build --------------------------------------------------
+// The CUDA library sqrt()/exp()/division carry slow-path branches, 64-bit immediates and selects
+// that cost more issue slots than FP64-pipe slots; the arguments here are known to be positive,
+// finite and (for exp) non-positive, so the kernels below keep only the fast paths.
+
+constexpr int kExpTab = 64;  // exp(t) = 2^k * 2^(j/64) * e^r,  |r| <= ln2/128
+
+// u = sqrt(d2), d2 > 0 (the caller seeds the accumulation with a tiny positive constant).
+// One MUFU.RSQ64H seed and a third-order correction: rel. error ~ 2 ulp.
+__device__ __forceinline__ double fast_sqrt(double d2)
+{
+    double y0;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(d2));
+    const double t1 = d2 * y0;               // ~ sqrt(d2)
+    const double e = fma(-t1, y0, 1.0);      // 1 - d2*y0^2
+    const double c = fma(e, 0.375, 0.5) * e; // e/2 + 3e^2/8
+    return fma(t1, c, t1);
+}
+__device__ __forceinline__ float fast_sqrt(float d2)
+{
+    float y0;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y0) : "f"(d2));
+    const float t1 = d2 * y0;
+    const float e = fmaf(-t1, y0, 1.0f);
+    return fmaf(t1 * 0.5f, e, t1);
+}
+
+// 1/x for a positive finite pivot: MUFU.RCP64H seed + cubic correction
+__device__ __forceinline__ double fast_rcp(double x)
+{
+    double r0;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r0) : "d"(x));
+    const double e = fma(-x, r0, 1.0);
+    const double r1 = fma(r0, fma(e, e, e), r0);
+    const double e1 = fma(-x, r1, 1.0);
+    return fma(r1, e1, r1);
+}
+__device__ __forceinline__ float fast_rcp(float x)
+{
+    float r0;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(x));
+    const float e = fmaf(-x, r0, 1.0f);
+    return fmaf(r0, e, r0);
+}
+
+// sigma2 * exp(-u) for u >= 0.  fp64: table of sigma2 * 2^(j/64) in shared memory (tab) + degree-5
+// polynomial on |r| <= ln2/128 (truncation 3e-17) -> 10 FP64 instructions instead of ~20 issue
+// slots more in exp().  u >= 708 (which includes the far-away sentinel rows) returns exactly 0.
+__device__ __forceinline__ double scaled_exp_neg(double u, const double *tab, double /*sigma2*/)
+{
+    const double kd = fma(u, -92.33248261689366, 6755399441055744.0);
+    const int ki = __double2loint(kd);
+    const double kf = kd - 6755399441055744.0;           // = round(-u * 64/ln2)
+    double r = fma(kf, -0.01083042469326756, -u);
+    r = fma(kf, -2.9815858269852933e-12, r);
+    double q = fma(r, 1.0 / 120.0, 1.0 / 24.0);
+    q = fma(r, q, 1.0 / 6.0);
+    q = fma(r, q, 0.5);
+    q = fma(r, q, 1.0);
+    const double tv = tab[ki & (kExpTab - 1)];
+    const double p = fma(tv * r, q, tv);                  // tv * (1 + r*q)
+    const int hi = __double2hiint(p) + ((ki >> 6) << 20); // * 2^k
+    const double v = __hiloint2double(hi, __double2loint(p));
+    return __double2hiint(u) >= 0x40862000 ? 0.0 : v;
+}
+__device__ __forceinline__ float scaled_exp_neg(float u, const float *, float sigma2)
+{
+    const float kf = rintf(u * -1.4426950408889634f);
+    float r = fmaf(kf, -0.693145751953125f, -u);
+    r = fmaf(kf, -1.428606765330187e-06f, r);
+    float e;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(r * 1.4426950408889634f));
+    const float v = sigma2 * e * __int_as_float((int(kf) + 127) << 23);
+    return u >= 87.0f ? 0.0f : v;
+}
+
+// sigma2 * rho(u), u = phi * distance (oracle: nngp_oracle.c corr()).
+template <typename T, int KERN>
+__device__ __forceinline__ T cov_from_u(T u, const T *tab, T sigma2)
+{
+    const T e = scaled_exp_neg(u, tab, sigma2);
+    if (KERN == NNGP_EXPONENTIAL) return e;
+    if (KERN == NNGP_MATERN32) return t_fma(u, e, e);
+    return t_fma(u, t_fma(u, T(1.0 / 3.0), T(1)), T(1)) * e;
+}
+
+// far-away sentinel for padded rows: every covariance with it underflows to exactly 0
+template <typename T> __device__ __forceinline__ T sentinel_coord(int r);
+template <> __device__ __forceinline__ double sentinel_coord<double>(int r) { return 1e100 * double(r + 1); }
+template <> __device__ __forceinline__ float sentinel_coord<float>(int r) { return 1e15f * float(r + 1); }
+template <typename T> __device__ __forceinline__ T tiny_seed();
+template <> __device__ __forceinline__ double tiny_seed<double>() { return 1e-290; }
+template <> __device__ __forceinline__ float tiny_seed<float>() { return 1e-36f; }
+
+template <typename T, int G>
+__device__ __forceinline__ T grp_bcast(T v, int src)
+{
+    return __shfl_sync(0xffffffffu, v, src, G);
+}
+
+// dynamic shared memory needed by one block
+template <typename T, int G, int R, bool DIM3>
+constexpr size_t smem_bytes(bool emit)
+{
+    constexpr int P = G * R;
+    constexpr int W = 32 / G;
+    size_t stage = size_t(kWarps) * W * P * sizeof(StagePt<T, DIM3>);
+    size_t dump = emit ? size_t(kWarps) * W * P * P * sizeof(T) : 0;
+    return kExpTab * sizeof(T) + stage + dump;
+}
+
+template <typename T, int G, int R, int KERN, bool DIM3, int MINB>
+__global__ void __launch_bounds__(kThreads, MINB) fused_loglik_kernel(const EvalArgs a)
+{
+    constexpr int P = G * R;   // rows of the augmented matrix
+    constexpr int W = 32 / G;  // locations per warp
+    using Pt = StagePt<T, DIM3>;
+
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T *exp_tab = reinterpret_cast<T *>(smem_raw);  // sigma2 * 2^(j/64) (fp64 path only)
+    Pt *stage_all = reinterpret_cast<Pt *>(smem_raw + kExpTab * sizeof(T));
+    T *dump_all = reinterpret_cast<T *>(smem_raw + kExpTab * sizeof(T) + size_t(kWarps) * W * P * sizeof(Pt));
+
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int q = lane % G;  // row residue owned by this lane
+    const int g = lane / G;  // location slot inside the warp
+    Pt *stage = stage_all + (size_t(warp) * W + g) * P;
+
+    const double *prm = a.params + size_t(blockIdx.y) * NNGP_NPARAM;
+    const T sigma2 = T(prm[0]);
+    const double phi = prm[1];
+    const double diag0 = prm[0] + prm[2];
+    const int m = a.m;
+    if (threadIdx.x < kExpTab) exp_tab[threadIdx.x] = T(prm[0] * exp2(double(threadIdx.x) / kExpTab));
+    __syncthreads();
+
+    double acc_log = 0.0, acc_quad = 0.0;
+    unsigned int acc_bad = 0;
+
+    const int64_t nloc = a.hi - a.lo;
+    const int64_t ngroups = (nloc + W - 1) / W;
+    for (int64_t grp = int64_t(blockIdx.x) * kWarps + warp; grp < ngroups;
+         grp += int64_t(gridDim.x) * kWarps) {
+        const int64_t i = a.lo + grp * W + g;
+        const bool live = i < a.hi;
+
+        // ---- gather: each lane fetches the records of the rows it owns -----------------------
+        // Coordinates are re-centred on the location and scaled by phi in fp64 before any cast,
+        // so neighbour differences keep full relative accuracy (also in fp32 mode) and the
+        // covariance build works directly on u^2 = (phi*d)^2.
+        double sx = 0.0, sy = 0.0, sz = 0.0;
+        if (live) {
+            const double2 *ps = reinterpret_cast<const double2 *>(a.pts + i);
+            const double2 s0 = __ldg(ps);
+            sx = s0.x; sy = s0.y;
+            if (DIM3) sz = __ldg(ps + 1).x;
+        }
+        T rx[R], ry[R], rz[R], w[R], dg[R];
+        bool valid[R];
+#pragma unroll
+        for (int s = 0; s < R; ++s) {
+            const int r = s * G + q;
+            int64_t idx = -1;
+            if (live) {
+                if (r == P - 1) idx = i;
+                else if (r < m) idx = __ldg(a.nbr + i * m + r);
+            }
+            valid[s] = idx >= 0;
+            double2 v0 = make_double2(0.0, 0.0), v1 = make_double2(0.0, 0.0);
+            double e2 = 0.0;
+            if (valid[s]) {
+                const double2 *pp = reinterpret_cast<const double2 *>(a.pts + idx);
+                v0 = __ldg(pp);
+                v1 = __ldg(pp + 1);
+                if (a.eps2) e2 = __ldg(a.eps2 + idx);
+            }
+            // padded rows sit at a far-away sentinel: all their covariances are exactly 0
+            rx[s] = valid[s] ? T((v0.x - sx) * phi) : sentinel_coord<T>(r);
+            ry[s] = valid[s] ? T((v0.y - sy) * phi) : T(0);
+            rz[s] = valid[s] ? T((v1.x - sz) * phi) : T(0);
+            w[s] = valid[s] ? T(v1.y) : T(0);
+            dg[s] = valid[s] ? T(diag0 + e2) : T(1);
+            Pt pt;
+            pt.x = rx[s]; pt.y = ry[s];
+            if constexpr (DIM3) { pt.z = rz[s]; pt.pad = T(0); }
+            stage[r] = pt;
+        }
+        __syncwarp();
+
+        // ---- stage 2: covariance build (lower triangle, row-owner layout) ----------------------
+        T A[R][P];
+#pragma unroll
+        for (int j = 0; j < P - 1; ++j) {
+            const Pt cj = stage[j];
+#pragma unroll
+            for (int s = 0; s < R; ++s) {
+                if (s * G + G - 1 > j) {
+                    const T dx = rx[s] - cj.x, dy = ry[s] - cj.y;
+                    T d2 = t_fma(dy, dy, t_fma(dx, dx, tiny_seed<T>()));
+                    if constexpr (DIM3) { const T dz = rz[s] - cj.z; d2 = t_fma(dz, dz, d2); }
+                    T v = cov_from_u<T, KERN>(fast_sqrt(d2), exp_tab, sigma2);
+                    if (j >= s * G) v = (s * G + q == j) ? dg[s] : v;  // diagonal block only
+                    A[s][j] = v;
+                }
+            }
+        }
+        A[R - 1][P - 1] = dg[R - 1];  // the location's own diagonal (owner: lane G-1)
+        __syncwarp();  // stage[] is rewritten by the next iteration
+
+        if (a.emit && live) {
+            // per-location covariance blocks (the _CNs/_Ccross/_Cs accessors; parity output)
+            const int64_t o = i - a.lo;
+#pragma unroll
+            for (int s = 0; s < R; ++s) {
+                const int r = s * G + q;
+#pragma unroll
+                for (int j = 0; j < P; ++j) {
+                    if (j >= (s + 1) * G || j > r) continue;
+                    const double v = valid[s] ? double(A[s][j]) : 0.0;
+                    if (r == P - 1) {
+                        if (j < m && a.cc) a.cc[o * m + j] = v;
+                        if (j == P - 1 && a.cs) a.cs[o] = v;
+                    } else if (r < m && a.CN) {
+                        a.CN[(o * m + r) * m + j] = v;
+                        a.CN[(o * m + j) * m + r] = v;
+                    }
+                }
+            }
+        }
+
+        // ---- stage 3: LDL^T elimination with the right-hand side carried along -----------------
+        bool bad = false;
+        T Flast = T(1), rlast = T(0);
+#pragma unroll
+        for (int k = 0; k < P; ++k) {
+            const T Dk = grp_bcast<T, G>(A[k / G][k], k % G);
+            const T wk = grp_bcast<T, G>(w[k / G], k % G);
+            bad |= !(Dk > T(0));
+            if (k == P - 1) {
+                Flast = Dk;
+                rlast = wk;
+            } else {
+                const T inv = fast_rcp(Dk);
+                T l[R];
+#pragma unroll
+                for (int s = 0; s < R; ++s) {
+                    if (s * G + G - 1 > k) {
+                        l[s] = A[s][k] * inv;
+                        w[s] = t_fma(-l[s], wk, w[s]);
+                    }
+                }
+                // (constant trip counts + guards: nvcc unrolls inner loops before the outer index is
+                // known, and a k-dependent bound would leave a rolled remainder that indexes A[]
+                // dynamically and demotes it to local memory)
+#pragma unroll
+                for (int j = 1; j < P; ++j) {
+                    if (j > k) {
+                        const T uj = grp_bcast<T, G>(A[j / G][k], j % G);
+#pragma unroll
+                        for (int s = 0; s < R; ++s)
+                            if (s * G + G - 1 >= j) A[s][j] = t_fma(-l[s], uj, A[s][j]);
+                    }
+                }
+#pragma unroll
+                for (int s = 0; s < R; ++s)
+                    if (s * G + G - 1 > k) A[s][k] = l[s];  // unit-lower factor (emit path)
+            }
+        }
+
+        if (live && q == 0) {
+            if (bad) {
+                acc_bad += 1u;
+            } else {
+                acc_log += log(double(Flast));
+                acc_quad += double(rlast) * double(rlast) / double(Flast);
+            }
+        }
+
+        if (a.emit) {
+            // b_i = L_N^{-T} ell, ell = last row of the unit-lower factor.  Rows travel through
+            // shared memory; one lane per location back-substitutes (parity / prediction output,
+            // not the metric's path).
+            T *dump = dump_all + (size_t(warp) * W + g) * P * P;
+#pragma unroll
+            for (int s = 0; s < R; ++s) {
+                const int r = s * G + q;
+#pragma unroll
+                for (int kk = 0; kk < P; ++kk)
+                    if (kk < (s + 1) * G && kk < r) dump[r * P + kk] = A[s][kk];
+            }
+            __syncwarp();
+            if (live && q == 0) {
+                const int64_t o = i - a.lo;
+                if (a.F) a.F[o] = bad ? nan("") : double(Flast);
+                if (a.B) {
+                    double b[P];
+                    for (int kk = P - 2; kk >= 0; --kk) {
+                        double v = double(dump[(P - 1) * P + kk]);
+                        for (int r = kk + 1; r < P - 1; ++r) v -= double(dump[r * P + kk]) * b[r];
+                        b[kk] = v;
+                    }
+                    for (int kk = 0; kk < m; ++kk) a.B[o * m + kk] = bad ? nan("") : b[kk];
+                }
+            }
+            __syncwarp();
+        }
+    }
+
+    // ---- reduction: warp shuffle tree -> block -> per-block partial -> last block sums ------
+    double bad_d = double(acc_bad);
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        acc_log += __shfl_xor_sync(0xffffffffu, acc_log, off);
+        acc_quad += __shfl_xor_sync(0xffffffffu, acc_quad, off);
+        bad_d += __shfl_xor_sync(0xffffffffu, bad_d, off);
+    }
+    __shared__ double red[kWarps][3];
+    __shared__ bool is_last;
+    if (lane == 0) { red[warp][0] = acc_log; red[warp][1] = acc_quad; red[warp][2] = bad_d; }
+    __syncthreads();
+    double *part = a.partials + size_t(blockIdx.y) * gridDim.x * 3;
+    if (threadIdx.x == 0) {
+        double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+        for (int wv = 0; wv < kWarps; ++wv) { s0 += red[wv][0]; s1 += red[wv][1]; s2 += red[wv][2]; }
+        part[size_t(blockIdx.x) * 3 + 0] = s0;
+        part[size_t(blockIdx.x) * 3 + 1] = s1;
+        part[size_t(blockIdx.x) * 3 + 2] = s2;
+        __threadfence();
+        const unsigned int ticket = atomicAdd(a.counters + blockIdx.y, 1u);
+        is_last = (ticket == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (is_last) {
+        __threadfence();
+        double t0 = 0.0, t1 = 0.0, t2 = 0.0;
+        for (unsigned int b = threadIdx.x; b < gridDim.x; b += kThreads) {
+            t0 += __ldcg(part + size_t(b) * 3 + 0);
+            t1 += __ldcg(part + size_t(b) * 3 + 1);
+            t2 += __ldcg(part + size_t(b) * 3 + 2);
+        }
+        __shared__ double fin[kThreads][3];
+        fin[threadIdx.x][0] = t0; fin[threadIdx.x][1] = t1; fin[threadIdx.x][2] = t2;
+        __syncthreads();
+        for (int stride = kThreads / 2; stride > 0; stride >>= 1) {
+            if (threadIdx.x < stride) {
+                fin[threadIdx.x][0] += fin[threadIdx.x + stride][0];
+                fin[threadIdx.x][1] += fin[threadIdx.x + stride][1];
+                fin[threadIdx.x][2] += fin[threadIdx.x + stride][2];
+            }
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) {
+            a.out[size_t(blockIdx.y) * 3 + 0] = fin[0][0];
+            a.out[size_t(blockIdx.y) * 3 + 1] = fin[0][1];
+            a.out[size_t(blockIdx.y) * 3 + 2] = fin[0][2];
+            a.counters[blockIdx.y] = 0u;  // ready for the next launch
+        }
+    }
+}
+
+// ---- host-side dispatch of one (T, KERN) family -------------------------------------------------
+template <typename T, int G, int R, int KERN, bool DIM3, int MINB>
+cudaError_t launch_one(const EvalArgs &a, int K, int grid_x, cudaStream_t stream)
+{
+    auto kern = fused_loglik_kernel<T, G, R, KERN, DIM3, MINB>;
+    const size_t smem = smem_bytes<T, G, R, DIM3>(a.emit != 0);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    kern<<<dim3(grid_x, K, 1), kThreads, smem, stream>>>(a);
+    return cudaGetLastError();
+}
+
+template <typename T, int G, int R, int KERN, bool DIM3, int MINB>
+int blocks_per_sm()
+{
+    auto kern = fused_loglik_kernel<T, G, R, KERN, DIM3, MINB>;
+    int nb = 0;
+    const size_t smem = smem_bytes<T, G, R, DIM3>(false);
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, kThreads, smem) != cudaSuccess) nb = 1;
+    return nb < 1 ? 1 : nb;
+}
+
+// row-count variants: (G, R) -> P = G*R >= m + 1
+//   m <= 7 : (4, 2)   m <= 15 : (4, 4)   m <= 31 : (16, 2)   m == 32 : (16, 3)
+#define NNGP_DISPATCH_SHAPE(T, KERN, DIM3, MINB4, MINB16, CALL)                   \
+    do {                                                                          \
+        if (m <= 7) { CALL(T, 4, 2, KERN, DIM3, MINB4); }                         \
+        else if (m <= 15) { CALL(T, 4, 4, KERN, DIM3, MINB4); }                   \
+        else if (m <= 31) { CALL(T, 16, 2, KERN, DIM3, MINB16); }                 \
+        else { CALL(T, 16, 3, KERN, DIM3, MINB16); }                              \
+    } while (0)
+
+template <typename T, int KERN>
+cudaError_t launch_family(int m, int D, const EvalArgs &a, int K, int grid_x, cudaStream_t stream)
+{
+    constexpr int MB4 = sizeof(T) == 8 ? 3 : 4;
+    constexpr int MB16 = sizeof(T) == 8 ? 2 : 4;
+#define NNGP_CALL_LAUNCH(T_, G_, R_, K_, D3_, MB_) return launch_one<T_, G_, R_, K_, D3_, MB_>(a, K, grid_x, stream)
+    if (D == 3) NNGP_DISPATCH_SHAPE(T, KERN, true, MB4, MB16, NNGP_CALL_LAUNCH);
+    else NNGP_DISPATCH_SHAPE(T, KERN, false, MB4, MB16, NNGP_CALL_LAUNCH);
+#undef NNGP_CALL_LAUNCH
+    return cudaErrorInvalidValue;
+}
+
+template <typename T, int KERN>
+int occupancy_family(int m, int D)
+{
+    constexpr int MB4 = sizeof(T) == 8 ? 3 : 4;
+    constexpr int MB16 = sizeof(T) == 8 ? 2 : 4;
+#define NNGP_CALL_OCC(T_, G_, R_, K_, D3_, MB_) return blocks_per_sm<T_, G_, R_, K_, D3_, MB_>()
+    if (D == 3) NNGP_DISPATCH_SHAPE(T, KERN, true, MB4, MB16, NNGP_CALL_OCC);
+    else NNGP_DISPATCH_SHAPE(T, KERN, false, MB4, MB16, NNGP_CALL_OCC);
+#undef NNGP_CALL_OCC
+    return 1;
+}
+
+inline int locations_per_warp(int m) { return m <= 15 ? 8 : 2; }
+
+}  // namespace nngp_fused
+
+// one translation unit per (dtype, kernel family) keeps nvcc parallel; each defines these two.
+#define NNGP_DEFINE_FAMILY(NAME, T, KERN)                                                         \
+    cudaError_t nngp_launch_##NAME(int m, int D, const EvalArgs &a, int K, int grid_x,            \
+                                   cudaStream_t stream)                                           \
+    {                                                                                             \
+        return nngp_fused::launch_family<T, KERN>(m, D, a, K, grid_x, stream);                    \
+    }                                                                                             \
+    int nngp_occupancy_##NAME(int m, int D) { return nngp_fused::occupancy_family<T, KERN>(m, D); }

@@ -1,0 +1,393 @@
+// nngp_api.cu -- the C ABI of libnngp_b200.so (include/nngp_b200.h): handle, uploads, dispatch.
+// No CPU fallback exists anywhere in this library: every compute entry point launches a kernel.
+#include <stdio.h>
+#include <string.h>
+
+#include <vector>
+
+#include "nngp_common.cuh"
+
+// one launcher/occupancy pair per (dtype, correlation family) translation unit
+#define NNGP_DECLARE_FAMILY(NAME)                                                                \
+    cudaError_t nngp_launch_##NAME(int m, int D, const EvalArgs &a, int K, int grid_x,           \
+                                   cudaStream_t stream);                                         \
+    int nngp_occupancy_##NAME(int m, int D);
+NNGP_DECLARE_FAMILY(f64_exp)
+NNGP_DECLARE_FAMILY(f64_m32)
+NNGP_DECLARE_FAMILY(f64_m52)
+NNGP_DECLARE_FAMILY(f32_exp)
+NNGP_DECLARE_FAMILY(f32_m32)
+NNGP_DECLARE_FAMILY(f32_m52)
+
+namespace {
+
+std::string g_create_error;
+
+int fail(nngp_handle *h, int code, const std::string &msg)
+{
+    if (h) h->err = msg; else g_create_error = msg;
+    return code;
+}
+
+int cuda_fail(nngp_handle *h, cudaError_t e, const char *what)
+{
+    return fail(h, NNGP_ECUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+
+#define CUDA_TRY(h, call)                                                  \
+    do {                                                                   \
+        cudaError_t e_ = (call);                                           \
+        if (e_ != cudaSuccess) return cuda_fail(h, e_, #call);             \
+    } while (0)
+
+template <typename P>
+void free_dev(P *&p)
+{
+    if (p) cudaFree(p);
+    p = nullptr;
+}
+
+int locations_per_warp(int m) { return m <= 15 ? 8 : 2; }
+
+int family_occupancy(int dtype, int kernel_id, int m, int D)
+{
+    if (dtype == NNGP_F64) {
+        if (kernel_id == NNGP_EXPONENTIAL) return nngp_occupancy_f64_exp(m, D);
+        if (kernel_id == NNGP_MATERN32) return nngp_occupancy_f64_m32(m, D);
+        return nngp_occupancy_f64_m52(m, D);
+    }
+    if (kernel_id == NNGP_EXPONENTIAL) return nngp_occupancy_f32_exp(m, D);
+    if (kernel_id == NNGP_MATERN32) return nngp_occupancy_f32_m32(m, D);
+    return nngp_occupancy_f32_m52(m, D);
+}
+
+cudaError_t family_launch(int dtype, int kernel_id, int m, int D, const EvalArgs &a, int K, int grid_x,
+                          cudaStream_t stream)
+{
+    if (dtype == NNGP_F64) {
+        if (kernel_id == NNGP_EXPONENTIAL) return nngp_launch_f64_exp(m, D, a, K, grid_x, stream);
+        if (kernel_id == NNGP_MATERN32) return nngp_launch_f64_m32(m, D, a, K, grid_x, stream);
+        return nngp_launch_f64_m52(m, D, a, K, grid_x, stream);
+    }
+    if (kernel_id == NNGP_EXPONENTIAL) return nngp_launch_f32_exp(m, D, a, K, grid_x, stream);
+    if (kernel_id == NNGP_MATERN32) return nngp_launch_f32_m32(m, D, a, K, grid_x, stream);
+    return nngp_launch_f32_m52(m, D, a, K, grid_x, stream);
+}
+
+// grid.x for nloc locations: enough resident blocks to fill every SM, never more than the work
+int grid_for(nngp_handle *h, int kernel_id, int64_t nloc)
+{
+    const int per_sm = family_occupancy(h->dtype, kernel_id, h->m, h->D);
+    const int64_t groups = (nloc + locations_per_warp(h->m) - 1) / locations_per_warp(h->m);
+    const int64_t need = (groups + 3) / 4;  // 4 warps per block
+    int64_t g = int64_t(h->num_sms) * per_sm;
+    if (g > need) g = need;
+    if (g < 1) g = 1;
+    return int(g);
+}
+
+int ensure_scratch(nngp_handle *h, int K, int grid)
+{
+    if (K > h->K_cap) {
+        free_dev(h->d_params); free_dev(h->d_out); free_dev(h->d_counters);
+        if (h->h_stage) { cudaFreeHost(h->h_stage); h->h_stage = nullptr; }
+        int cap = K < 16 ? 16 : K;
+        CUDA_TRY(h, cudaMalloc(&h->d_params, sizeof(double) * NNGP_NPARAM * cap));
+        CUDA_TRY(h, cudaMalloc(&h->d_out, sizeof(double) * NNGP_NSTAT * cap));
+        CUDA_TRY(h, cudaMalloc(&h->d_counters, sizeof(unsigned int) * cap));
+        CUDA_TRY(h, cudaMemset(h->d_counters, 0, sizeof(unsigned int) * cap));
+        CUDA_TRY(h, cudaMallocHost(&h->h_stage, sizeof(double) * (NNGP_NPARAM + NNGP_NSTAT) * cap));
+        free_dev(h->d_partials);
+        h->grid_cap = 0;
+        h->K_cap = cap;
+    }
+    if (grid > h->grid_cap || !h->d_partials) {
+        free_dev(h->d_partials);
+        int gc = grid < 1024 ? 1024 : grid;
+        CUDA_TRY(h, cudaMalloc(&h->d_partials, sizeof(double) * 3 * size_t(gc) * h->K_cap));
+        h->grid_cap = gc;
+    }
+    return NNGP_OK;
+}
+
+int check_eval(nngp_handle *h, int kernel_id, const void *params, int K)
+{
+    if (!h) return fail(nullptr, NNGP_EINVAL, "null handle");
+    if (!h->pts) return fail(h, NNGP_ESTATE, "nngp_set_data has not been called");
+    if (!h->has_nbr) return fail(h, NNGP_ESTATE, "no neighbour table: call nngp_build_neighbors or nngp_set_neighbors");
+    if (kernel_id < 0 || kernel_id > NNGP_MATERN52) return fail(h, NNGP_EINVAL, "unknown kernel_id");
+    if (!params || K < 1) return fail(h, NNGP_EINVAL, "params must hold K >= 1 parameter vectors");
+    return NNGP_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *nngp_version(void) { return "nngp_b200 0.1 (sm_100a)"; }
+
+const char *nngp_last_error(const nngp_handle *h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int nngp_create(nngp_handle **out, int device, int dtype)
+{
+    if (!out) return fail(nullptr, NNGP_EINVAL, "null handle pointer");
+    *out = nullptr;
+    if (dtype != NNGP_F64 && dtype != NNGP_F32) return fail(nullptr, NNGP_EINVAL, "dtype must be NNGP_F64 or NNGP_F32");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(nullptr, NNGP_ENODEVICE,
+                    std::string("no CUDA device (this library has no CPU fallback): ") +
+                        (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0"));
+    if (device < 0 || device >= ndev) return fail(nullptr, NNGP_EINVAL, "device index out of range");
+    cudaDeviceProp prop;
+    if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) return cuda_fail(nullptr, e, "cudaGetDeviceProperties");
+    if (prop.major != 10)
+        return fail(nullptr, NNGP_ENODEVICE, "libnngp_b200 is built for sm_100a only; device is sm_" +
+                                                 std::to_string(prop.major) + std::to_string(prop.minor));
+    if ((e = cudaSetDevice(device)) != cudaSuccess) return cuda_fail(nullptr, e, "cudaSetDevice");
+    nngp_handle *h = new nngp_handle();
+    h->device = device;
+    h->dtype = dtype;
+    h->num_sms = prop.multiProcessorCount;
+    if ((e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) {
+        delete h;
+        return cuda_fail(nullptr, e, "cudaStreamCreate");
+    }
+    if ((e = cudaMalloc(&h->d_tile_counter, sizeof(unsigned int))) != cudaSuccess) {
+        cudaStreamDestroy(h->stream);
+        delete h;
+        return cuda_fail(nullptr, e, "cudaMalloc");
+    }
+    *out = h;
+    return NNGP_OK;
+}
+
+void nngp_destroy(nngp_handle *h)
+{
+    if (!h) return;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    free_dev(h->pts); free_dev(h->eps2); free_dev(h->nbr);
+    free_dev(h->d_params); free_dev(h->d_out); free_dev(h->d_partials);
+    free_dev(h->d_counters); free_dev(h->d_tile_counter);
+    if (h->h_stage) cudaFreeHost(h->h_stage);
+    cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+int nngp_set_data(nngp_handle *h, const double *coords, int64_t n, int D, const double *y, const double *eps2)
+{
+    if (!h) return fail(nullptr, NNGP_EINVAL, "null handle");
+    if (!coords || !y) return fail(h, NNGP_EINVAL, "coords and y must not be NULL");
+    if (n < 1 || n > 2147483647LL) return fail(h, NNGP_EINVAL, "n must be in [1, 2^31)");
+    if (D < 1 || D > NNGP_MAX_D) return fail(h, NNGP_EINVAL, "D must be 1, 2 or 3");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    free_dev(h->pts); free_dev(h->eps2); free_dev(h->nbr);
+    h->has_nbr = false; h->m = 0;
+    h->n = n; h->D = D; h->lo = 0; h->hi = n;
+    // pack {x, y, z, yval} records on the host, one upload
+    std::vector<double4> rec((size_t)n);
+    for (int64_t i = 0; i < n; ++i) {
+        const double *c = coords + i * D;
+        rec[(size_t)i] = make_double4(c[0], D > 1 ? c[1] : 0.0, D > 2 ? c[2] : 0.0, y[i]);
+    }
+    CUDA_TRY(h, cudaMalloc(&h->pts, sizeof(double4) * (size_t)n));
+    CUDA_TRY(h, cudaMemcpyAsync(h->pts, rec.data(), sizeof(double4) * (size_t)n, cudaMemcpyHostToDevice, h->stream));
+    if (eps2) {
+        CUDA_TRY(h, cudaMalloc(&h->eps2, sizeof(double) * (size_t)n));
+        CUDA_TRY(h, cudaMemcpyAsync(h->eps2, eps2, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, h->stream));
+    }
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return NNGP_OK;
+}
+
+int nngp_set_y(nngp_handle *h, const double *y)
+{
+    if (!h) return fail(nullptr, NNGP_EINVAL, "null handle");
+    if (!h->pts) return fail(h, NNGP_ESTATE, "nngp_set_data has not been called");
+    if (!y) return fail(h, NNGP_EINVAL, "y must not be NULL");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    // strided copy into the .w lane of the records
+    CUDA_TRY(h, cudaMemcpy2DAsync(reinterpret_cast<double *>(h->pts) + 3, sizeof(double4), y, sizeof(double),
+                                  sizeof(double), (size_t)h->n, cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return NNGP_OK;
+}
+
+int nngp_set_shard(nngp_handle *h, int64_t lo, int64_t hi)
+{
+    if (!h) return fail(nullptr, NNGP_EINVAL, "null handle");
+    if (!h->pts) return fail(h, NNGP_ESTATE, "nngp_set_data has not been called");
+    if (lo < 0 || hi < lo || hi > h->n) return fail(h, NNGP_EINVAL, "shard must satisfy 0 <= lo <= hi <= n");
+    h->lo = lo; h->hi = hi;
+    return NNGP_OK;
+}
+
+static int alloc_nbr(nngp_handle *h, int m)
+{
+    if (m < 1 || m > NNGP_MAX_M) return fail(h, NNGP_EINVAL, "m must be in [1, 32]");
+    if (h->nbr && h->m != m) free_dev(h->nbr);
+    if (!h->nbr) CUDA_TRY(h, cudaMalloc(&h->nbr, sizeof(int32_t) * (size_t)h->n * m));
+    h->m = m;
+    return NNGP_OK;
+}
+
+int nngp_build_neighbors(nngp_handle *h, int m, int tile_offset, int tile_stride)
+{
+    if (!h) return fail(nullptr, NNGP_EINVAL, "null handle");
+    if (!h->pts) return fail(h, NNGP_ESTATE, "nngp_set_data has not been called");
+    if (tile_stride < 1 || tile_offset < 0 || tile_offset >= tile_stride)
+        return fail(h, NNGP_EINVAL, "need 0 <= tile_offset < tile_stride");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    int rc = alloc_nbr(h, m);
+    if (rc) return rc;
+    CUDA_TRY(h, launch_knn_ordered(h, m, tile_offset, tile_stride, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    h->has_nbr = true;
+    return NNGP_OK;
+}
+
+int nngp_set_neighbors(nngp_handle *h, const int32_t *idx, int m)
+{
+    if (!h) return fail(nullptr, NNGP_EINVAL, "null handle");
+    if (!h->pts) return fail(h, NNGP_ESTATE, "nngp_set_data has not been called");
+    if (!idx) return fail(h, NNGP_EINVAL, "idx must not be NULL");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    int rc = alloc_nbr(h, m);
+    if (rc) return rc;
+    CUDA_TRY(h, cudaMemcpyAsync(h->nbr, idx, sizeof(int32_t) * (size_t)h->n * m, cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    h->has_nbr = true;
+    return NNGP_OK;
+}
+
+int nngp_get_neighbors(nngp_handle *h, int32_t *out)
+{
+    if (!h) return fail(nullptr, NNGP_EINVAL, "null handle");
+    if (!h->has_nbr) return fail(h, NNGP_ESTATE, "no neighbour table");
+    if (!out) return fail(h, NNGP_EINVAL, "out must not be NULL");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    CUDA_TRY(h, cudaMemcpyAsync(out, h->nbr, sizeof(int32_t) * (size_t)h->n * h->m, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return NNGP_OK;
+}
+
+void *nngp_neighbors_device_ptr(nngp_handle *h) { return (h && h->has_nbr) ? (void *)h->nbr : nullptr; }
+
+int nngp_loglik_device(nngp_handle *h, int kernel_id, const double *d_params, int K, double *d_out, void *stream)
+{
+    int rc = check_eval(h, kernel_id, d_params, K);
+    if (rc) return rc;
+    if (!d_out) return fail(h, NNGP_EINVAL, "d_out must not be NULL");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+    const int64_t nloc = h->hi - h->lo;
+    if (nloc == 0) {  // empty shard: the statistics are exactly zero
+        CUDA_TRY(h, cudaMemsetAsync(d_out, 0, sizeof(double) * NNGP_NSTAT * K, st));
+        return NNGP_OK;
+    }
+    const int grid = grid_for(h, kernel_id, nloc);
+    if ((rc = ensure_scratch(h, K, grid))) return rc;
+    EvalArgs a{};
+    a.pts = h->pts; a.eps2 = h->eps2; a.nbr = h->nbr;
+    a.lo = h->lo; a.hi = h->hi; a.m = h->m;
+    a.params = d_params; a.partials = h->d_partials; a.counters = h->d_counters; a.out = d_out;
+    a.emit = 0;
+    CUDA_TRY(h, family_launch(h->dtype, kernel_id, h->m, h->D, a, K, grid, st));
+    ++h->launches;
+    return NNGP_OK;
+}
+
+int nngp_loglik(nngp_handle *h, int kernel_id, const double *params, int K, double *out)
+{
+    int rc = check_eval(h, kernel_id, params, K);
+    if (rc) return rc;
+    if (!out) return fail(h, NNGP_EINVAL, "out must not be NULL");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    if ((rc = ensure_scratch(h, K, 1))) return rc;
+    double *hp = h->h_stage, *ho = h->h_stage + size_t(NNGP_NPARAM) * h->K_cap;
+    memcpy(hp, params, sizeof(double) * NNGP_NPARAM * K);
+    CUDA_TRY(h, cudaMemcpyAsync(h->d_params, hp, sizeof(double) * NNGP_NPARAM * K, cudaMemcpyHostToDevice, h->stream));
+    if ((rc = nngp_loglik_device(h, kernel_id, h->d_params, K, h->d_out, h->stream))) return rc;
+    CUDA_TRY(h, cudaMemcpyAsync(ho, h->d_out, sizeof(double) * NNGP_NSTAT * K, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    memcpy(out, ho, sizeof(double) * NNGP_NSTAT * K);
+    return NNGP_OK;
+}
+
+// shared by nngp_factors / nngp_cov_blocks: run the emitting variant over [i0, i1) in slabs
+static int run_emit(nngp_handle *h, int kernel_id, const double *params, int64_t i0, int64_t i1, double *B,
+                    double *F, double *CN, double *cc, double *cs)
+{
+    int rc = check_eval(h, kernel_id, params, 1);
+    if (rc) return rc;
+    if (i0 < 0 || i1 < i0 || i1 > h->n) return fail(h, NNGP_EINVAL, "need 0 <= i0 <= i1 <= n");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    const int m = h->m;
+    const int64_t slab = CN ? 65536 : 1 << 20;
+    const int64_t cap = (i1 - i0) < slab ? (i1 - i0) : slab;
+    if (cap == 0) return NNGP_OK;
+    double *dB = nullptr, *dF = nullptr, *dCN = nullptr, *dcc = nullptr, *dcs = nullptr;
+    auto cleanup = [&]() { free_dev(dB); free_dev(dF); free_dev(dCN); free_dev(dcc); free_dev(dcs); };
+#define EMIT_TRY(call)                                                         \
+    do {                                                                       \
+        cudaError_t e_ = (call);                                               \
+        if (e_ != cudaSuccess) { cleanup(); return cuda_fail(h, e_, #call); }  \
+    } while (0)
+    if (B) EMIT_TRY(cudaMalloc(&dB, sizeof(double) * cap * m));
+    if (F) EMIT_TRY(cudaMalloc(&dF, sizeof(double) * cap));
+    if (CN) EMIT_TRY(cudaMalloc(&dCN, sizeof(double) * cap * m * m));
+    if (cc) EMIT_TRY(cudaMalloc(&dcc, sizeof(double) * cap * m));
+    if (cs) EMIT_TRY(cudaMalloc(&dcs, sizeof(double) * cap));
+    if ((rc = ensure_scratch(h, 1, grid_for(h, kernel_id, cap)))) { cleanup(); return rc; }
+    memcpy(h->h_stage, params, sizeof(double) * NNGP_NPARAM);
+    EMIT_TRY(cudaMemcpyAsync(h->d_params, h->h_stage, sizeof(double) * NNGP_NPARAM, cudaMemcpyHostToDevice, h->stream));
+    for (int64_t s0 = i0; s0 < i1; s0 += cap) {
+        const int64_t s1 = s0 + cap < i1 ? s0 + cap : i1;
+        const int64_t cnt = s1 - s0;
+        EvalArgs a{};
+        a.pts = h->pts; a.eps2 = h->eps2; a.nbr = h->nbr;
+        a.lo = s0; a.hi = s1; a.m = m;
+        a.params = h->d_params; a.partials = h->d_partials; a.counters = h->d_counters; a.out = h->d_out;
+        a.emit = 1; a.B = dB; a.F = dF; a.CN = dCN; a.cc = dcc; a.cs = dcs;
+        if (dCN) EMIT_TRY(cudaMemsetAsync(dCN, 0, sizeof(double) * cnt * m * m, h->stream));
+        if (dcc) EMIT_TRY(cudaMemsetAsync(dcc, 0, sizeof(double) * cnt * m, h->stream));
+        EMIT_TRY(family_launch(h->dtype, kernel_id, m, h->D, a, 1, grid_for(h, kernel_id, cnt), h->stream));
+        ++h->launches;
+        const int64_t o = s0 - i0;
+        if (B) EMIT_TRY(cudaMemcpyAsync(B + o * m, dB, sizeof(double) * cnt * m, cudaMemcpyDeviceToHost, h->stream));
+        if (F) EMIT_TRY(cudaMemcpyAsync(F + o, dF, sizeof(double) * cnt, cudaMemcpyDeviceToHost, h->stream));
+        if (CN) EMIT_TRY(cudaMemcpyAsync(CN + o * m * m, dCN, sizeof(double) * cnt * m * m, cudaMemcpyDeviceToHost, h->stream));
+        if (cc) EMIT_TRY(cudaMemcpyAsync(cc + o * m, dcc, sizeof(double) * cnt * m, cudaMemcpyDeviceToHost, h->stream));
+        if (cs) EMIT_TRY(cudaMemcpyAsync(cs + o, dcs, sizeof(double) * cnt, cudaMemcpyDeviceToHost, h->stream));
+        EMIT_TRY(cudaStreamSynchronize(h->stream));
+    }
+#undef EMIT_TRY
+    cleanup();
+    return NNGP_OK;
+}
+
+int nngp_factors(nngp_handle *h, int kernel_id, const double *params, int64_t i0, int64_t i1, double *B, double *F)
+{
+    return run_emit(h, kernel_id, params, i0, i1, B, F, nullptr, nullptr, nullptr);
+}
+
+int nngp_cov_blocks(nngp_handle *h, int kernel_id, const double *params, int64_t i0, int64_t i1, double *CN,
+                    double *cc, double *cs)
+{
+    return run_emit(h, kernel_id, params, i0, i1, nullptr, nullptr, CN, cc, cs);
+}
+
+int64_t nngp_launch_count(const nngp_handle *h) { return h ? h->launches : 0; }
+
+int nngp_measure_fma_peak(nngp_handle *h, int dtype, int iters, double *instr_per_s)
+{
+    if (!h) return fail(nullptr, NNGP_EINVAL, "null handle");
+    if (!instr_per_s || iters < 1) return fail(h, NNGP_EINVAL, "bad arguments");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    CUDA_TRY(h, launch_fma_peak(h, dtype, iters, instr_per_s));
+    return NNGP_OK;
+}
+
+}  // extern "C"

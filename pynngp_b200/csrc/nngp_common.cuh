@@ -1,0 +1,70 @@
+// nngp_common.cuh -- shared declarations of libnngp_b200.so (sm_100a only).
+//
+// Data layout in HBM (per handle, one B200):
+//   pts   n x double4 {x, y, z, yval}   32-byte records: one L2 sector per neighbour gather,
+//                                       and a contiguous byte range per candidate tile for the
+//                                       k-NN's bulk (TMA 1-D) copies.  z = 0 when D < 3, y = 0 when D < 2.
+//   eps2  n x double (optional)         per-observation variance added to the diagonal.
+//   nbr   n x m int32, row-major        neighbour table, -1 padded, valid entries first.
+// Coordinates and y are replicated on every GPU; a handle evaluates rows [lo, hi) only.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+
+#include "../../include/nngp_b200.h"
+
+struct nngp_handle {
+    int device = 0;
+    int dtype = NNGP_F64;
+    int num_sms = 0;
+    cudaStream_t stream = nullptr;
+
+    int64_t n = 0;
+    int D = 0;
+    int m = 0;
+    int64_t lo = 0, hi = 0;
+
+    double4 *pts = nullptr;
+    double *eps2 = nullptr;
+    int32_t *nbr = nullptr;
+    bool has_nbr = false;
+
+    // evaluation scratch (grown on demand)
+    int K_cap = 0;
+    int grid_cap = 0;
+    double *d_params = nullptr;    // K_cap x 4
+    double *d_out = nullptr;       // K_cap x 3
+    double *d_partials = nullptr;  // K_cap x grid_cap x 3
+    unsigned int *d_counters = nullptr;  // K_cap tickets for the last-block reduction
+    unsigned int *d_tile_counter = nullptr;
+    double *h_stage = nullptr;     // pinned: K_cap x (4 + 3)
+
+    int64_t launches = 0;
+    std::string err;
+};
+
+// Arguments of the fused covariance + factorisation + reduction kernel.
+struct EvalArgs {
+    const double4 *pts;
+    const double *eps2;   // nullable
+    const int32_t *nbr;   // n x m
+    int64_t lo, hi;       // rows to evaluate
+    int m;
+    const double *params;     // gridDim.y x 4 (device)
+    double *partials;         // gridDim.y x gridDim.x x 3
+    unsigned int *counters;   // gridDim.y
+    double *out;              // gridDim.y x 3
+    // optional per-location outputs (rows lo..hi map to output rows 0..hi-lo); any may be null
+    int emit;                 // 0: reduction only
+    double *B, *F, *CN, *cc, *cs;
+};
+
+// launchers implemented in the .cu files; each returns the cudaError of the launch.
+cudaError_t launch_fused_loglik(nngp_handle *h, int kernel_id, const EvalArgs &a, int K,
+                                cudaStream_t stream);
+cudaError_t launch_knn_ordered(nngp_handle *h, int m, int tile_offset, int tile_stride,
+                               cudaStream_t stream);
+cudaError_t launch_fma_peak(nngp_handle *h, int dtype, int iters, double *instr_per_s);
+int fused_grid_blocks(nngp_handle *h, int kernel_id, int64_t nloc);

@@ -1,0 +1,225 @@
+"""``NNGP`` -- the reference's public class (pyNNGP/nngp.py:5-101), same constructor and attributes,
+with the hot path running on a B200 through libnngp_b200.so.
+
+What is kept from the reference (drop-in contract):
+  * ``NNGP(t, y, eps, refType, m, cov)`` positional, all work done eagerly (nngp.py:6-18);
+  * attributes ``t, y, eps, refType, m, cov, s, wt, ws, Ns, Nt``; ``s is t`` and ``Nt is Ns`` for
+    ``refType == 'S=T'`` (nngp.py:31, 65-67); ``Ns[0] == []`` and ``Ns[i]`` an int64 array of the
+    min(m, i) nearest predecessors in ascending distance (nngp.py:49-62);
+  * the per-location accessors ``_CNs, _Ccross, _Cs, _Bsi, _Fsi`` (nngp.py:73-96) -- stubs upstream,
+    real values here; ``oneSample`` (nngp.py:98-101) calls undefined methods upstream and raises
+    ``NotImplementedError`` here.
+What is added: ``loglik``, ``loglik_terms``, ``loglik_batch``, ``factors`` and keyword-only engine
+options.  There is no CPU fallback: constructing an ``NNGP`` without a B200 raises.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import _lib, dist as _dist
+from .kernels import Kernel, parse as _parse_cov
+
+LOG_2PI = float(np.log(2.0 * np.pi))
+
+
+class NeighborSets:
+    """Read-only sequence with the reference's ``Ns`` layout (nngp.py:50-62) over the dense
+    (n, m) int32 table: ``Ns[0] == []``; ``Ns[i]`` is an int64 array, ascending distance."""
+
+    def __init__(self, table):
+        self.table = table
+
+    def __len__(self):
+        return self.table.shape[0]
+
+    def __getitem__(self, i):
+        if isinstance(i, slice):
+            return [self[k] for k in range(*i.indices(len(self)))]
+        if i < 0:
+            i += len(self)
+        if i == 0:
+            return []  # the reference appends a Python list for the first site (nngp.py:52-54)
+        row = self.table[i]
+        return row[row >= 0].astype(np.int64)
+
+    def __iter__(self):
+        return (self[i] for i in range(len(self)))
+
+
+class NNGP(object):
+    def __init__(self, t, y, eps, refType, m, cov, *, dtype="float64", device=None, neighbors=None,
+                 group=None):
+        self.t = t  # ordinates
+        self.y = y  # abscissae
+        self.eps = eps  # measurement uncertainties in y
+        self.refType = refType  # type of reference set to construct
+        self.m = m  # number of reference neighbors per point
+        self.cov = cov  # covariance of the parent GP: kernel spec (see pynngp_b200.kernels)
+
+        self._kernel: Kernel = _parse_cov(cov)
+        self._group = group
+        self._rank, self._world = _dist.get_world(group)
+        if device is None:
+            device = self._local_device()
+        self._engine = _lib.Engine(device=device, dtype=dtype)
+        self._ycol = None
+        self._timings = {}
+
+        self._init_s()
+        self._init_wt()
+        self._upload()
+        self._make_s_neighbor_sets(neighbors)
+        self._make_t_neighbor_sets()
+        self._ws = None
+
+    # ---- construction steps, named as in the reference -----------------------------------------
+    def _local_device(self):
+        import os
+
+        return int(os.environ.get("LOCAL_RANK", "0")) if self._world > 1 else 0
+
+    def _init_s(self):
+        # nngp.py:21-40.  Only 'S=T' works upstream (the tuple branches read an unset attribute,
+        # nngp.py:34); they change the model to a latent NNGP and are out of the likelihood path.
+        if isinstance(self.refType, str) and self.refType == "S=T":
+            self.s = self.t
+        else:
+            raise NotImplementedError("only refType='S=T' is supported (the reference's other branches crash)")
+
+    def _init_wt(self):
+        self.wt = np.copy(self.y)  # nngp.py:42-43
+
+    def _upload(self):
+        s = np.ascontiguousarray(self.s, dtype=np.float64)
+        if s.ndim == 1:
+            s = s[:, None]
+        if not np.isfinite(s).all():
+            raise ValueError("coordinates must be finite")
+        n = s.shape[0]
+        y = np.asarray(self.y, dtype=np.float64)
+        self._y2d = y.reshape(n, -1)
+        eps = np.broadcast_to(np.asarray(self.eps, dtype=np.float64).reshape((n, -1) if np.ndim(self.eps) else (1, 1)),
+                              self._y2d.shape)
+        self._eps2 = None if not np.any(eps) else np.ascontiguousarray(eps * eps)
+        self._coords = s
+        self._set_column(0)
+        lo, hi = _dist.shard_bounds(n, self._rank, self._world)
+        self._engine.set_shard(lo, hi)
+        self._shard = (lo, hi)
+
+    def _set_column(self, c):
+        if self._ycol == c:
+            return
+        eps2 = None if self._eps2 is None else np.ascontiguousarray(self._eps2[:, c])
+        if self._ycol is None or self._eps2 is not None:
+            had_table = self._engine.m > 0
+            table = self._table if had_table else None
+            self._engine.set_data(self._coords, np.ascontiguousarray(self._y2d[:, c]), eps2)
+            if had_table:
+                self._engine.set_neighbors(table)
+                self._engine.set_shard(*self._shard)
+        else:
+            self._engine.set_y(np.ascontiguousarray(self._y2d[:, c]))
+        self._ycol = c
+
+    def _make_s_neighbor_sets(self, neighbors=None):
+        # nngp.py:49-62 -> stage 1 on the GPU (or an injected (n, m) table)
+        import time
+
+        eng = self._engine
+        t0 = time.perf_counter()
+        if neighbors is not None:
+            eng.set_neighbors(neighbors)
+        elif self._world == 1:
+            eng.build_neighbors(self.m)
+        else:
+            import torch
+
+            off, stride = _dist.knn_tile_split(self._rank, self._world)
+            eng.build_neighbors(self.m, off, stride)
+            view = _dist.DevicePtrView(eng.neighbors_device_ptr(), (eng.n, eng.m), "<i4")
+            tab = torch.as_tensor(view, device=f"cuda:{eng.device}")
+            _dist.assemble_table_max(tab, self._group)
+            torch.cuda.synchronize(eng.device)
+        self._timings["knn_s"] = time.perf_counter() - t0
+        self._table = eng.get_neighbors()
+        self.Ns = NeighborSets(self._table)
+
+    def _make_t_neighbor_sets(self):
+        self.Nt = self.Ns  # nngp.py:65-67
+
+    @property
+    def ws(self):
+        # nngp.py:45-47: 5-NN uniform-mean warm start of the latent field (Gibbs state, not used by
+        # the likelihood).  Not on the hot path; not built yet.
+        raise NotImplementedError("ws (Gibbs warm start, nngp.py:45-47) is outside the likelihood hot path")
+
+    # ---- parameters -------------------------------------------------------------------------------
+    def _params(self, sigma2=None, phi=None, tau2=None):
+        return np.array(self._kernel.params(sigma2, phi, tau2), dtype=np.float64)
+
+    # ---- the reference's per-location accessors (nngp.py:73-96) ------------------------------------
+    def _p(self, i):
+        return int((self._table[i] >= 0).sum())
+
+    def _CNs(self, i, **kw):
+        """C_{N(s_i)} (nngp.py:78-82): (p, p)."""
+        CN, _, _ = self._engine.cov_blocks(self._kernel.kernel_id, self._params(**kw), i, i + 1)
+        p = self._p(i)
+        return CN[0, :p, :p]
+
+    def _Ccross(self, i, **kw):
+        """C_{s_i, N(s_i)} (nngp.py:84-86): (p,)."""
+        _, cc, _ = self._engine.cov_blocks(self._kernel.kernel_id, self._params(**kw), i, i + 1)
+        return cc[0, : self._p(i)]
+
+    def _Cs(self, i, **kw):
+        """C_{s_i, s_i} (nngp.py:92-96)."""
+        _, _, cs = self._engine.cov_blocks(self._kernel.kernel_id, self._params(**kw), i, i + 1)
+        return float(cs[0])
+
+    def _Bsi(self, i, **kw):
+        """B_{s_i} = C_N(i)^{-1} c_i (nngp.py:73-76): (p,)."""
+        B, _ = self._engine.factors(self._kernel.kernel_id, self._params(**kw), i, i + 1, want_F=False)
+        return B[0, : self._p(i)]
+
+    def _Fsi(self, i, **kw):
+        """F_{s_i} = C(i,i) - c_i^T b_i (nngp.py:88-90)."""
+        _, F = self._engine.factors(self._kernel.kernel_id, self._params(**kw), i, i + 1, want_B=False)
+        return float(F[0])
+
+    def factors(self, sigma2=None, phi=None, tau2=None, i0=0, i1=None):
+        """(B (i1-i0, m) zero padded, F (i1-i0,)) for rows [i0, i1)."""
+        return self._engine.factors(self._kernel.kernel_id, self._params(sigma2, phi, tau2), i0, i1)
+
+    # ---- the likelihood ----------------------------------------------------------------------------
+    def loglik_batch(self, params):
+        """params (K, 3|4) rows of (sigma2, phi, tau2[, nu]) -> (K, 3) global statistics
+        [sum log F, sum r^2/F, n_bad], summed over response columns and over all ranks."""
+        params = np.atleast_2d(np.asarray(params, dtype=np.float64))
+        if params.shape[1] == 3:
+            params = np.concatenate([params, np.zeros((params.shape[0], 1))], axis=1)
+        total = np.zeros((params.shape[0], _lib.NSTAT))
+        for c in range(self._y2d.shape[1]):
+            self._set_column(c)
+            total += self._engine.loglik(self._kernel.kernel_id, params)
+        if self._world > 1:
+            total = _dist.allreduce_stats(total, self._group)
+        return total
+
+    def loglik_terms(self, sigma2=None, phi=None, tau2=None):
+        """(sum_i log F_i, sum_i r_i^2 / F_i) -- the reduction BASELINE.json's north_star names."""
+        st = self.loglik_batch(self._params(sigma2, phi, tau2)[None, :])[0]
+        if st[2] > 0:
+            raise FloatingPointError(f"{int(st[2])} location(s) had a non-positive-definite neighbour covariance")
+        return float(st[0]), float(st[1])
+
+    def loglik(self, sigma2=None, phi=None, tau2=None):
+        """log N(y; 0, C_nngp)."""
+        slog, squad = self.loglik_terms(sigma2, phi, tau2)
+        ncol = self._y2d.shape[1]
+        return -0.5 * (slog + squad) - 0.5 * len(self._coords) * ncol * LOG_2PI
+
+    def oneSample(self):
+        # nngp.py:98-101 calls update_wt / update_ws / update_y_unobserved, none of which exist upstream
+        raise NotImplementedError("the reference's Gibbs sweep is unimplemented upstream (nngp.py:98-101)")

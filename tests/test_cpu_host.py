@@ -1,0 +1,138 @@
+"""CPU tests of the host side (no GPU): the C-ABI library loads and exports every symbol the header
+declares, the shard arithmetic, kernel-spec parsing, the NeighborSets view, and the multi-rank
+combination over gloo (world_size 2)."""
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from oracle import nngp_oracle as orc
+from pynngp_b200 import _lib, kernels
+from pynngp_b200.dist import shard_bounds
+from pynngp_b200.nngp import NeighborSets
+from pynngp_b200.synthetic import synthetic
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def built_lib():
+    if not os.path.exists(_lib.LIB_PATH):
+        from pynngp_b200.build import build
+
+        build()
+    return _lib.load()
+
+
+def test_library_exports_every_declared_symbol(built_lib):
+    header = open(os.path.join(ROOT, "include", "nngp_b200.h")).read()
+    declared = set(re.findall(r"\b(nngp_[a-z0-9_]+)\s*\(", header))
+    declared.discard("nngp_handle")
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    for name in declared:
+        assert hasattr(built_lib, name)
+    assert b"sm_100a" in built_lib.nngp_version()
+
+
+def test_no_cpu_fallback_without_device(built_lib):
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(_lib.NNGPError, match="no CPU fallback"):
+        _lib.Engine(0)
+
+
+def test_product_never_imports_oracle():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "pynngp_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in src and "from oracle" not in src and "liboracle" not in src, f
+
+
+def test_shard_bounds_cover_exactly():
+    for n in (0, 1, 7, 1000, 10**6 + 3):
+        for world in (1, 2, 3, 4, 8):
+            edges = [shard_bounds(n, r, world) for r in range(world)]
+            assert edges[0][0] == 0 and edges[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(edges[:-1], edges[1:]))
+            sizes = [hi - lo for lo, hi in edges]
+            assert max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        shard_bounds(10, 2, 2)
+
+
+def test_kernel_spec_parsing():
+    assert kernels.parse(None).kernel_id == 0
+    assert kernels.parse("matern32").kernel_id == 1
+    assert kernels.parse(("matern", 2.5)).kernel_id == 2
+    assert kernels.parse(("exponential",)).kernel_id == 0
+    assert kernels.Matern(1.5, 1.0, 6.0, 0.1).params() == [1.0, 6.0, 0.1, 0.0]
+    assert kernels.Exponential(1.0, 6.0, 0.1).params(phi=3.0) == [1.0, 3.0, 0.1, 0.0]
+    with pytest.raises(TypeError):
+        kernels.parse(lambda a, b: 0.0)
+    with pytest.raises(ValueError):
+        kernels.Matern(0.7)
+    with pytest.raises(ValueError):
+        kernels.parse(None).params()
+
+
+def test_neighbor_sets_view_matches_reference_layout(golden_dir):
+    g = np.load(os.path.join(golden_dir, "ns_test_init_shape.npz"))
+    Ns = NeighborSets(g["Ns"])
+    assert len(Ns) == 200 and Ns[0] == []
+    assert Ns[1].dtype == np.int64 and Ns[1].tolist() == [0]
+    assert len(Ns[2]) == 2 and len(Ns[199]) == 3
+    for i in range(200):
+        assert i not in Ns[i]  # the reference's own assertion, tests/test_init.py:22-23
+    assert g["coords"][Ns[7]].shape == (3, 2)
+
+
+_WORKER = r'''
+import os, sys
+import numpy as np
+import torch.distributed as dist
+sys.path.insert(0, os.environ["NNGP_ROOT"])
+from oracle import nngp_oracle as orc
+from pynngp_b200.dist import shard_bounds, allreduce_stats, assemble_table_max, get_world
+from pynngp_b200.synthetic import synthetic
+
+dist.init_process_group("gloo")
+rank, world = get_world()
+s, y = synthetic(2000, 2, 3)
+m = 9
+# stage 1 split by tiles dealt from the heavy end, assembled with an elementwise MAX
+full = orc.c_knn_ordered(s, m)
+tile = 128
+ntiles = (len(s) + tile - 1) // tile
+mine = np.full_like(full, -2)
+for t in range(ntiles):
+    if (ntiles - 1 - t) % world == rank:
+        mine[t * tile:(t + 1) * tile] = full[t * tile:(t + 1) * tile]
+table = assemble_table_max(mine)
+assert np.array_equal(table, full)
+# stages 2-3: contiguous shard per rank, partial statistics summed by allreduce
+lo, hi = shard_bounds(len(s), rank, world)
+part = np.array([orc.c_loglik(s, y, table, 1, 1.0, 6.0, 0.1, lo=lo, hi=hi)])
+tot = allreduce_stats(part)
+want = np.array(orc.c_loglik(s, y, full, 1, 1.0, 6.0, 0.1))
+np.testing.assert_allclose(tot[0], want, rtol=1e-12)
+dist.destroy_process_group()
+print("rank", rank, "ok")
+'''
+
+
+def test_two_rank_gloo_combination(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(_WORKER)
+    env = dict(os.environ, NNGP_ROOT=ROOT, MASTER_ADDR="127.0.0.1")
+    r = subprocess.run(
+        [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+         "--master-addr", "127.0.0.1", "--master-port", "29617", str(script)],
+        env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert r.stdout.count("ok") == 2

@@ -1,0 +1,306 @@
+"""GPU parity tests (run on the B200 box: pytest -m gpu).  Every call goes through the C ABI
+(pynngp_b200._lib.Engine -> libnngp_b200.so) or the drop-in class on top of it; the oracle
+(oracle/) and the golden fixtures (tests/golden/) are the checkers.
+
+Tolerances (BASELINE.json north_star): neighbour index sets bit-exact; b_i, F_i and the
+log-likelihood statistics within 1e-10 relative in fp64 and 1e-4 in fp32.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import nngp_oracle as orc
+from pynngp_b200 import _lib
+from pynngp_b200.synthetic import CONFIGS, PARAMS, synthetic
+
+pytestmark = pytest.mark.gpu
+
+RTOL64 = 1e-10
+RTOL32 = 1e-4
+P0 = np.array([PARAMS["sigma2"], PARAMS["phi"], PARAMS["tau2"], 0.0])
+KIDS = {"exponential": 0, "matern32": 1, "matern52": 2}
+
+
+def engine(s, y, eps2=None, dtype="float64"):
+    e = _lib.Engine(0, dtype)
+    e.set_data(s, y, eps2)
+    return e
+
+
+# ---- stage 1: ordered k-NN ------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["test_init_shape", "cfg1", "d2_m15", "d3_m30", "d1_m5", "d3_m32"])
+def test_knn_matches_reference_golden(golden_dir, name):
+    g = np.load(os.path.join(golden_dir, f"ns_{name}.npz"))
+    s = g["coords"]
+    e = engine(s, np.zeros(len(s)))
+    e.build_neighbors(int(g["m"]))
+    assert np.array_equal(e.get_neighbors(), g["Ns"])  # bit-exact incl. order and -1 padding
+
+
+def test_knn_lattice_ties(golden_dir):
+    g = np.load(os.path.join(golden_dir, "ns_lattice.npz"))
+    s, m = g["coords"], int(g["m"])
+    e = engine(s, np.zeros(len(s)))
+    e.build_neighbors(m)
+    got = e.get_neighbors()
+    assert np.array_equal(got, orc.c_knn_ordered(s, m))  # the engine's (d2, j) rule, exactly
+    ref = g["Ns"]
+    for i in range(len(s)):  # vs the reference: same distance multiset per row
+        a, b = got[i][got[i] >= 0], ref[i][ref[i] >= 0]
+        assert np.array_equal(np.sort(orc.np_dist2(s[i], s[a])), np.sort(orc.np_dist2(s[i], s[b])))
+
+
+def test_knn_duplicates_and_tiny_n():
+    s = np.array([[0.5, 0.5]] * 6 + [[0.25, 0.5]] * 3)
+    e = engine(s, np.zeros(len(s)))
+    e.build_neighbors(4)
+    assert np.array_equal(e.get_neighbors(), orc.c_knn_ordered(s, 4))
+    e1 = engine(np.array([[0.1, 0.2]]), np.zeros(1))
+    e1.build_neighbors(3)
+    assert e1.get_neighbors().tolist() == [[-1, -1, -1]]
+
+
+@pytest.mark.parametrize("n,D,m", [(20000, 2, 15), (9000, 3, 30), (5000, 1, 7), (1537, 2, 32)])
+def test_knn_matches_oracle_mid_size(n, D, m):
+    s, y = synthetic(n, D, 100 + D)
+    e = engine(s, y)
+    e.build_neighbors(m)
+    got = e.get_neighbors()
+    want = orc.c_knn_ordered(s, m, threads=os.cpu_count() or 1)
+    assert np.array_equal(got, want)
+
+
+def test_knn_tile_split_assembles():
+    s, y = synthetic(3000, 2, 9)
+    e = engine(s, y)
+    e.build_neighbors(10)
+    full = e.get_neighbors()
+    parts = []
+    for off in range(3):
+        e.build_neighbors(10, off, 3)
+        parts.append(e.get_neighbors())
+    for p in parts:
+        assert ((p == full) | (p == _lib.ROW_UNSET)).all()
+    assert np.array_equal(np.maximum.reduce(parts), full)
+    # each row is owned by exactly one rank
+    owned = sum((p[:, 0] != _lib.ROW_UNSET).astype(int) for p in parts)
+    assert (owned == 1).all()
+
+
+# ---- stages 2-3 -----------------------------------------------------------------------------------
+CASES = [  # n, D, m, kernel
+    (1000, 2, 10, "exponential"),   # cfg1
+    (800, 2, 15, "matern32"),       # cfg3's shape
+    (700, 3, 30, "matern32"),       # cfg4's shape
+    (500, 1, 3, "matern52"),
+    (600, 3, 7, "exponential"),
+    (400, 2, 20, "matern52"),
+    (300, 3, 32, "exponential"),
+    (300, 2, 31, "matern32"),
+    (200, 2, 1, "exponential"),
+]
+
+
+@pytest.mark.parametrize("n,D,m,kernel", CASES)
+def test_cov_blocks_factors_loglik_fp64(n, D, m, kernel):
+    s, y = synthetic(n, D, 31 + m)
+    kid = KIDS[kernel]
+    eps2 = np.linspace(0.0, 0.02, n)
+    nbr = orc.c_knn_ordered(s, m)
+    e = engine(s, y, eps2)
+    e.set_neighbors(nbr)
+    prm = np.array([1.3, 5.0, 0.07, 0.0])
+    CN, cc, cs = e.cov_blocks(kid, prm)
+    CN0, cc0, cs0 = orc.c_cov_blocks(s, nbr, kid, *prm[:3], eps2=eps2)
+    np.testing.assert_allclose(CN, CN0, rtol=1e-12, atol=1e-300)
+    np.testing.assert_allclose(cc, cc0, rtol=1e-12, atol=1e-300)
+    np.testing.assert_allclose(cs, cs0, rtol=1e-15)
+    B, F = e.factors(kid, prm)
+    B0, F0 = orc.c_factors(s, y, nbr, kid, *prm[:3], eps2=eps2)
+    scale = np.maximum(np.abs(B0).max(axis=1, keepdims=True), 1.0)
+    assert (np.abs(B - B0) / scale).max() <= RTOL64
+    np.testing.assert_allclose(F, F0, rtol=RTOL64)
+    st = e.loglik(kid, prm)[0]
+    st0 = orc.c_loglik(s, y, nbr, kid, *prm[:3], eps2=eps2)
+    assert st[2] == 0 and st0[2] == 0
+    np.testing.assert_allclose(st[:2], st0[:2], rtol=RTOL64)
+
+
+@pytest.mark.parametrize("n,D,m,kernel", CASES[:4])
+def test_loglik_fp32(n, D, m, kernel):
+    s, y = synthetic(n, D, 31 + m)
+    kid = KIDS[kernel]
+    nbr = orc.c_knn_ordered(s, m)
+    e = engine(s, y, None, "float32")
+    e.set_neighbors(nbr)
+    st = e.loglik(kid, P0)[0]
+    st0 = orc.c_loglik(s, y, nbr, kid, *P0[:3])
+    np.testing.assert_allclose(st[:2], st0[:2], rtol=RTOL32)
+    B, F = e.factors(kid, P0)
+    B0, F0 = orc.c_factors(s, y, nbr, kid, *P0[:3])
+    scale = np.maximum(np.abs(B0).max(axis=1, keepdims=True), 1.0)
+    assert (np.abs(B - B0) / scale).max() <= RTOL32
+    np.testing.assert_allclose(F, F0, rtol=RTOL32)
+
+
+def test_batched_params_and_determinism():
+    s, y = synthetic(5000, 2, 8)
+    nbr = orc.c_knn_ordered(s, 15, threads=4)
+    e = engine(s, y)
+    e.set_neighbors(nbr)
+    rng = np.random.default_rng(0)
+    prm = np.stack([rng.uniform(0.5, 2, 6), rng.uniform(3, 30, 6), rng.uniform(0.01, 0.5, 6), np.zeros(6)], 1)
+    st = e.loglik(1, prm)
+    for k in range(6):
+        one = e.loglik(1, prm[k])[0]
+        assert np.array_equal(one, st[k])  # same grid -> bitwise identical
+        st0 = orc.c_loglik(s, y, nbr, 1, *prm[k, :3])
+        np.testing.assert_allclose(st[k, :2], st0[:2], rtol=RTOL64)
+
+
+def test_shards_sum_to_whole_and_empty_shard():
+    s, y = synthetic(10007, 2, 12)
+    nbr = orc.c_knn_ordered(s, 15, threads=4)
+    e = engine(s, y)
+    e.set_neighbors(nbr)
+    whole = e.loglik(1, P0)[0]
+    from pynngp_b200.dist import shard_bounds
+
+    for world in (2, 4, 8):
+        acc = np.zeros(3)
+        for r in range(world):
+            e.set_shard(*shard_bounds(len(s), r, world))
+            acc += e.loglik(1, P0)[0]
+        np.testing.assert_allclose(acc[:2], whole[:2], rtol=1e-12)
+    e.set_shard(5, 5)
+    assert np.array_equal(e.loglik(1, P0)[0], np.zeros(3))
+    # shard parity against the oracle on the same rows
+    e.set_shard(1234, 4321)
+    st0 = orc.c_loglik(s, y, nbr, 1, *P0[:3], lo=1234, hi=4321)
+    np.testing.assert_allclose(e.loglik(1, P0)[0][:2], st0[:2], rtol=RTOL64)
+
+
+def test_dense_gp_identity_through_engine():
+    """m = n-1 = 31: the NNGP density equals the exact GP density (known answer)."""
+    n = 32
+    s, y = synthetic(n, 2, 77)
+    e = engine(s, y)
+    e.build_neighbors(n - 1)
+    for kid in (0, 1, 2):
+        st = e.loglik(kid, P0)[0]
+        ll = orc.loglik_from_terms(st[0], st[1], n)
+        exact = orc.dense_gp_loglik(s, y, kid, *P0[:3])
+        assert abs(ll - exact) <= 1e-11 * abs(exact)
+
+
+def test_non_spd_counted_not_nan():
+    s = np.array([[0.0, 0.0], [0.0, 0.0], [0.0, 0.0], [1.0, 1.0], [0.5, 0.5]])
+    y = np.ones(5)
+    e = engine(s, y)
+    e.build_neighbors(3)
+    st = e.loglik(0, np.array([1.0, 1.0, 0.0, 0.0]))[0]
+    st0 = orc.c_loglik(s, y, e.get_neighbors(), 0, 1.0, 1.0, 0.0)
+    assert st[2] >= 1 and np.isfinite(st[:2]).all()
+    assert st[2] == st0[2]
+
+
+def test_set_y_replaces_response():
+    s, y = synthetic(3000, 2, 3)
+    nbr = orc.c_knn_ordered(s, 8)
+    e = engine(s, y)
+    e.set_neighbors(nbr)
+    y2 = np.cos(7 * y)
+    e.set_y(y2)
+    st0 = orc.c_loglik(s, y2, nbr, 0, *P0[:3])
+    np.testing.assert_allclose(e.loglik(0, P0)[0][:2], st0[:2], rtol=RTOL64)
+
+
+def test_error_behaviour():
+    e = _lib.Engine(0)
+    with pytest.raises(_lib.NNGPError):
+        e.loglik(0, P0)  # no data yet
+    s, y = synthetic(100, 2, 1)
+    e.set_data(s, y)
+    with pytest.raises(_lib.NNGPError):
+        e.loglik(0, P0)  # no neighbours yet
+    with pytest.raises(_lib.NNGPError):
+        e.build_neighbors(33)
+    with pytest.raises(_lib.NNGPError):
+        e.set_data(np.zeros((10, 4)), np.zeros(10))  # D > 3
+
+
+# ---- the drop-in class ---------------------------------------------------------------------------
+def test_reference_own_test_headless():
+    """tests/test_init.py of the reference, body reproduced against the new class (plot dropped):
+    n=200 uniform 2-D sites, y and eps of shape (n, 2), m=3, cov=None."""
+    import pyNNGP
+
+    n = 200
+    rng = np.random.default_rng(1234)
+    t = np.vstack([rng.uniform(size=n), rng.uniform(size=n)]).T
+    y = np.zeros_like(t)
+    eps = np.ones_like(t) * 0.001
+    nngp = pyNNGP.NNGP(t, y, eps, "S=T", 3, None)
+    for i in range(n):
+        assert i not in nngp.Ns[i]
+    assert nngp.s is t and nngp.Nt is nngp.Ns and nngp.Ns[0] == []
+    assert nngp.Ns[5].dtype == np.int64 and len(nngp.Ns[2]) == 2
+    assert nngp.s[nngp.Ns[7]].shape == (3, 2)
+    assert np.array_equal(nngp.wt, y)
+
+
+def test_class_cfg1_end_to_end():
+    import pyNNGP
+    from pynngp_b200 import Exponential
+
+    c = CONFIGS["cfg1"]
+    s, y = synthetic(c["n"], c["D"], c["seed"])
+    obj = pyNNGP.NNGP(s, y, 0.0, "S=T", c["m"], Exponential(**PARAMS))
+    want_tab = orc.c_knn_ordered(s, c["m"])
+    assert np.array_equal(obj._table, want_tab)
+    npo = orc.NumpyNNGP(s, y, want_tab, 0, *P0[:3])
+    for i in (0, 1, 5, 10, 500, 999):
+        np.testing.assert_allclose(obj._CNs(i), npo._CNs(i).reshape(obj._CNs(i).shape), rtol=1e-12)
+        np.testing.assert_allclose(obj._Ccross(i), npo._Ccross(i), rtol=1e-12)
+        assert obj._Cs(i) == npo._Cs(i)
+        np.testing.assert_allclose(obj._Bsi(i), npo._Bsi(i), rtol=1e-9, atol=1e-12)
+        np.testing.assert_allclose(obj._Fsi(i), npo._Fsi(i), rtol=RTOL64)
+    slog, squad, _ = orc.c_loglik(s, y, want_tab, 0, *P0[:3])
+    got = obj.loglik_terms()
+    np.testing.assert_allclose(got, (slog, squad), rtol=RTOL64)
+    np.testing.assert_allclose(obj.loglik(), orc.loglik_from_terms(slog, squad, c["n"]), rtol=RTOL64)
+    with pytest.raises(TypeError):
+        pyNNGP.NNGP(s, y, 0.0, "S=T", 3, lambda a, b: 1.0)
+    with pytest.raises(NotImplementedError):
+        obj.oneSample()
+
+
+# ---- full-size properties (no oracle at this size) -----------------------------------------------
+def test_cfg3_full_size_properties():
+    c = CONFIGS["cfg3"]
+    s, y = synthetic(c["n"], c["D"], c["seed"])
+    e = engine(s, y)
+    e.build_neighbors(c["m"])
+    tab = e.get_neighbors()
+    n, m = tab.shape
+    rows = np.arange(n)[:, None]
+    assert (tab[m:] >= 0).all() and (tab < rows).all()                # predecessors only
+    assert all((tab[i, :i] >= 0).all() and (tab[i, i:] == -1).all() for i in range(m))  # ragged head
+    d2 = ((s[tab[m:]] - s[m:, None, :]) ** 2).sum(-1)
+    assert (np.diff(d2, axis=1) >= 0).all()                           # ascending distance
+    # spot rows against the oracle's exact scan
+    for i in (15, 16, 4097, 123456, 999999):
+        assert np.array_equal(tab[i], orc.c_knn_ordered(s, m, lo=i, hi=i + 1)[i])
+    whole = e.loglik(1, P0)[0]
+    assert whole[2] == 0
+    acc = np.zeros(3)
+    for r in range(8):
+        lo, hi = (n * r) // 8, (n * (r + 1)) // 8
+        e.set_shard(lo, hi)
+        acc += e.loglik(1, P0)[0]
+    np.testing.assert_allclose(acc[:2], whole[:2], rtol=1e-12)        # shards sum to the whole
+    lo, hi = 500000, 540000                                           # a slab against the oracle
+    e.set_shard(lo, hi)
+    st0 = orc.c_loglik(s, y, tab, 1, *P0[:3], lo=lo, hi=hi, threads=os.cpu_count() or 1)
+    np.testing.assert_allclose(e.loglik(1, P0)[0][:2], st0[:2], rtol=RTOL64)
