@@ -190,7 +190,8 @@ def run_ours(args, cfg):
     d_prm = torch.tensor(prm_host, dtype=torch.float64, device="cuda")
     d_out = torch.zeros((1, 3), dtype=torch.float64, device="cuda")
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream()  # a real stream: the C ABI treats NULL as 'the handle's own stream'
+    torch.cuda.set_stream(stream)
 
     def step_device():
         eng.loglik_device(kid, d_prm.data_ptr(), 1, d_out.data_ptr(), stream.cuda_stream)

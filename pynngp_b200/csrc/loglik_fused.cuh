@@ -251,7 +251,9 @@ __global__ void __launch_bounds__(kThreads, MINB) fused_loglik_kernel(const Eval
                 }
             }
         }
-        A[R - 1][P - 1] = dg[R - 1];  // the location's own diagonal (owner: lane G-1)
+        // the last column of each diagonal block only carries lane G-1's diagonal entry
+#pragma unroll
+        for (int s = 0; s < R; ++s) A[s][s * G + G - 1] = dg[s];
         __syncwarp();  // stage[] is rewritten by the next iteration
 
         if (a.emit && live) {
