@@ -22,6 +22,7 @@
 // a 16x16 / 32x32 factorisation with a serial pivot chain plus transcendental covariance entries.
 #pragma once
 #include <math.h>
+#include <stdlib.h>
 
 #include "nngp_common.cuh"
 
@@ -130,6 +131,69 @@ __device__ __forceinline__ T cov_from_u(T u, const T *tab, T sigma2)
     return t_fma(u, t_fma(u, T(1.0 / 3.0), T(1)), T(1)) * e;
 }
 
+// The same arithmetic for a batch of B independent pairs, written stage by stage so that the
+// instruction stream interleaves B dependency chains (the per-pair chain is ~20 dependent FP64
+// operations; with 3 resident warps per scheduler a single chain leaves the FP64 pipe idle).
+// In: x[b] = u_b^2 > 0.  Out: x[b] = sigma2 * rho(u_b).
+template <int KERN, int B>
+__device__ __forceinline__ void cov_batch(double (&x)[B], const double *tab, double)
+{
+    double y0[B], t1[B], e[B], u[B], kd[B], r[B], qq[B], tv[B];
+    int ki[B];
+#pragma unroll
+    for (int b = 0; b < B; ++b) asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y0[b]) : "d"(x[b]));
+#pragma unroll
+    for (int b = 0; b < B; ++b) t1[b] = x[b] * y0[b];
+#pragma unroll
+    for (int b = 0; b < B; ++b) e[b] = fma(-t1[b], y0[b], 1.0);
+#pragma unroll
+    for (int b = 0; b < B; ++b) y0[b] = fma(e[b], 0.375, 0.5);
+#pragma unroll
+    for (int b = 0; b < B; ++b) y0[b] = y0[b] * e[b];
+#pragma unroll
+    for (int b = 0; b < B; ++b) u[b] = fma(t1[b], y0[b], t1[b]);
+#pragma unroll
+    for (int b = 0; b < B; ++b) kd[b] = fma(u[b], -92.33248261689366, 6755399441055744.0);
+#pragma unroll
+    for (int b = 0; b < B; ++b) { ki[b] = __double2loint(kd[b]); kd[b] = kd[b] - 6755399441055744.0; }
+#pragma unroll
+    for (int b = 0; b < B; ++b) tv[b] = tab[ki[b] & (kExpTab - 1)];
+#pragma unroll
+    for (int b = 0; b < B; ++b) r[b] = fma(kd[b], -0.01083042469326756, -u[b]);
+#pragma unroll
+    for (int b = 0; b < B; ++b) r[b] = fma(kd[b], -2.9815858269852933e-12, r[b]);
+#pragma unroll
+    for (int b = 0; b < B; ++b) qq[b] = fma(r[b], 1.0 / 120.0, 1.0 / 24.0);
+#pragma unroll
+    for (int b = 0; b < B; ++b) qq[b] = fma(r[b], qq[b], 1.0 / 6.0);
+#pragma unroll
+    for (int b = 0; b < B; ++b) qq[b] = fma(r[b], qq[b], 0.5);
+#pragma unroll
+    for (int b = 0; b < B; ++b) qq[b] = fma(r[b], qq[b], 1.0);
+#pragma unroll
+    for (int b = 0; b < B; ++b) r[b] = tv[b] * r[b];
+#pragma unroll
+    for (int b = 0; b < B; ++b) r[b] = fma(r[b], qq[b], tv[b]);
+#pragma unroll
+    for (int b = 0; b < B; ++b) {
+        const int hi = __double2hiint(r[b]) + ((ki[b] >> 6) << 20);
+        const double v = __hiloint2double(hi, __double2loint(r[b]));
+        e[b] = __double2hiint(u[b]) >= 0x40862000 ? 0.0 : v;
+    }
+#pragma unroll
+    for (int b = 0; b < B; ++b) {
+        if (KERN == NNGP_EXPONENTIAL) x[b] = e[b];
+        else if (KERN == NNGP_MATERN32) x[b] = fma(u[b], e[b], e[b]);
+        else x[b] = fma(u[b], fma(u[b], 1.0 / 3.0, 1.0), 1.0) * e[b];
+    }
+}
+template <int KERN, int B>
+__device__ __forceinline__ void cov_batch(float (&x)[B], const float *tab, float sigma2)
+{
+#pragma unroll
+    for (int b = 0; b < B; ++b) x[b] = cov_from_u<float, KERN>(fast_sqrt(x[b]), tab, sigma2);
+}
+
 // far-away sentinel for padded rows: every covariance with it underflows to exactly 0
 template <typename T> __device__ __forceinline__ T sentinel_coord(int r);
 template <> __device__ __forceinline__ double sentinel_coord<double>(int r) { return 1e100 * double(r + 1); }
@@ -138,21 +202,48 @@ template <typename T> __device__ __forceinline__ T tiny_seed();
 template <> __device__ __forceinline__ double tiny_seed<double>() { return 1e-290; }
 template <> __device__ __forceinline__ float tiny_seed<float>() { return 1e-36f; }
 
+__device__ __forceinline__ uint32_t smem_addr(const void *p)
+{
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
 template <typename T, int G>
 __device__ __forceinline__ T grp_bcast(T v, int src)
 {
     return __shfl_sync(0xffffffffu, v, src, G);
 }
 
+// entries of the strict lower triangle a lane parks: row block s holds columns 0 .. (s+1)*G-2
+template <int G, int R>
+__host__ __device__ constexpr int tile_entries() { return G * R * (R + 1) / 2 - R; }
+template <int G>
+__host__ __device__ constexpr int tile_offset(int s) { return G * s * (s + 1) / 2 - s; }
+
+// Per-warp shared-memory carve-up (bytes).  Everything a warp touches is private to it, so the
+// main loop needs __syncwarp only.
+template <typename T, int G, int R, bool DIM3>
+struct WarpSmem {
+    static constexpr int P = G * R, W = 32 / G;
+    // location strides are padded by 16 bytes so the W groups of a warp start in different banks
+    // (unpadded, all groups alias: 8-way conflicts on every record / coordinate access)
+    static constexpr int rec_stride = P * 32 + 16;                        // bytes per location
+    static constexpr int stage_stride = P * int(sizeof(StagePt<T, DIM3>)) + 16;
+    static constexpr size_t rec = size_t(W) * rec_stride;                 // gathered {x,y,z,yval} records
+    static constexpr size_t e2 = DIM3 ? size_t(W) * P * sizeof(double) : 0;  // gathered eps2 (D = 3 only;
+                                                                             // D < 3 records carry it in .z)
+    static constexpr size_t idx = size_t(R) * 32 * sizeof(int);          // next group's neighbour indices
+    static constexpr size_t acc = size_t(3) * 32 * sizeof(double);       // per-lane partial sums
+    static constexpr size_t tile = size_t(32) * tile_entries<G, R>() * sizeof(T);  // parked matrix rows
+    static constexpr size_t stage = size_t(W) * stage_stride;                      // scaled coordinates
+    static constexpr size_t dump = size_t(P) * P * sizeof(T);            // emit only: one location's factor
+    __host__ __device__ static constexpr size_t total(bool emit) { return rec + e2 + idx + acc + tile + stage + (emit ? dump : 0); }
+};
+
 // dynamic shared memory needed by one block
 template <typename T, int G, int R, bool DIM3>
 constexpr size_t smem_bytes(bool emit)
 {
-    constexpr int P = G * R;
-    constexpr int W = 32 / G;
-    size_t stage = size_t(kWarps) * W * P * sizeof(StagePt<T, DIM3>);
-    size_t dump = emit ? size_t(kWarps) * W * P * P * sizeof(T) : 0;
-    return kExpTab * sizeof(T) + stage + dump;
+    return kExpTab * sizeof(double) + size_t(kWarps) * WarpSmem<T, G, R, DIM3>::total(emit);
 }
 
 template <typename T, int G, int R, int KERN, bool DIM3, int MINB>
@@ -161,17 +252,24 @@ __global__ void __launch_bounds__(kThreads, MINB) fused_loglik_kernel(const Eval
     constexpr int P = G * R;   // rows of the augmented matrix
     constexpr int W = 32 / G;  // locations per warp
     using Pt = StagePt<T, DIM3>;
+    using WS = WarpSmem<T, G, R, DIM3>;
 
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    T *exp_tab = reinterpret_cast<T *>(smem_raw);  // sigma2 * 2^(j/64) (fp64 path only)
-    Pt *stage_all = reinterpret_cast<Pt *>(smem_raw + kExpTab * sizeof(T));
-    T *dump_all = reinterpret_cast<T *>(smem_raw + kExpTab * sizeof(T) + size_t(kWarps) * W * P * sizeof(Pt));
-
+    extern __shared__ __align__(32) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const int q = lane % G;  // row residue owned by this lane
     const int g = lane / G;  // location slot inside the warp
-    Pt *stage = stage_all + (size_t(warp) * W + g) * P;
+
+    T *exp_tab = reinterpret_cast<T *>(smem_raw);  // sigma2 * 2^(j/64) (fp64 path only)
+    unsigned char *wbase = smem_raw + kExpTab * sizeof(double) + size_t(warp) * WS::total(a.emit != 0);
+    unsigned char *recbuf = wbase + g * WS::rec_stride;  // this location's records (16-byte aligned)
+    double *e2buf = reinterpret_cast<double *>(wbase + WS::rec);
+    int *idxbuf = reinterpret_cast<int *>(wbase + WS::rec + WS::e2) + lane;          // [s * 32]
+    volatile double *accbuf = reinterpret_cast<volatile double *>(wbase + WS::rec + WS::e2 + WS::idx) + lane;
+    // lane-minor layout: entry e of this lane sits at tile[e * 32] -> conflict-free, no sync needed
+    volatile T *tile = reinterpret_cast<volatile T *>(wbase + WS::rec + WS::e2 + WS::idx + WS::acc) + lane;
+    Pt *stage = reinterpret_cast<Pt *>(wbase + WS::rec + WS::e2 + WS::idx + WS::acc + WS::tile + g * WS::stage_stride);
+    T *dump = reinterpret_cast<T *>(wbase + WS::rec + WS::e2 + WS::idx + WS::acc + WS::tile + WS::stage);
 
     const double *prm = a.params + size_t(blockIdx.y) * NNGP_NPARAM;
     const T sigma2 = T(prm[0]);
@@ -179,82 +277,148 @@ __global__ void __launch_bounds__(kThreads, MINB) fused_loglik_kernel(const Eval
     const double diag0 = prm[0] + prm[2];
     const int m = a.m;
     if (threadIdx.x < kExpTab) exp_tab[threadIdx.x] = T(prm[0] * exp2(double(threadIdx.x) / kExpTab));
-    __syncthreads();
-
-    double acc_log = 0.0, acc_quad = 0.0;
-    unsigned int acc_bad = 0;
+    accbuf[0] = 0.0; accbuf[32] = 0.0; accbuf[64] = 0.0;  // sum log F, sum r^2/F, n_bad: rarely touched,
+    __syncthreads();                                        // kept out of the register file
 
     const int64_t nloc = a.hi - a.lo;
     const int64_t ngroups = (nloc + W - 1) / W;
-    for (int64_t grp = int64_t(blockIdx.x) * kWarps + warp; grp < ngroups;
-         grp += int64_t(gridDim.x) * kWarps) {
-        const int64_t i = a.lo + grp * W + g;
-        const bool live = i < a.hi;
+    const int64_t gstride = int64_t(gridDim.x) * kWarps;
+    const int64_t grp0 = int64_t(blockIdx.x) * kWarps + warp;
 
-        // ---- gather: each lane fetches the records of the rows it owns -----------------------
-        // Coordinates are re-centred on the location and scaled by phi in fp64 before any cast,
-        // so neighbour differences keep full relative accuracy (also in fp32 mode) and the
-        // covariance build works directly on u^2 = (phi*d)^2.
-        double sx = 0.0, sy = 0.0, sz = 0.0;
-        if (live) {
-            const double2 *ps = reinterpret_cast<const double2 *>(a.pts + i);
-            const double2 s0 = __ldg(ps);
-            sx = s0.x; sy = s0.y;
-            if (DIM3) sz = __ldg(ps + 1).x;
-        }
-        T rx[R], ry[R], rz[R], w[R], dg[R];
-        bool valid[R];
+    // ---- software-pipelined gather, all through cp.async (LDGSTS) ---------------------------------
+    // While group t is being built and eliminated, the 32-byte records of group t+1 and the
+    // neighbour indices of group t+2 are in flight global -> shared.  Nothing loop-carried ever waits
+    // on a global load: at the top of an iteration one cp.async.wait_group covers copies that were
+    // issued a whole iteration earlier.
+    auto issue_idx = [&](int64_t grp) {  // indices of `grp` -> idxbuf (own slots only)
+        const int64_t i = a.lo + grp * W + g;
+        const bool live = grp < ngroups && i < a.hi;
 #pragma unroll
         for (int s = 0; s < R; ++s) {
             const int r = s * G + q;
-            int64_t idx = -1;
-            if (live) {
-                if (r == P - 1) idx = i;
-                else if (r < m) idx = __ldg(a.nbr + i * m + r);
+            if (live && r < m && r != P - 1) {
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_addr(idxbuf + s * 32)),
+                             "l"(a.nbr + i * m + r)
+                             : "memory");
+            } else {
+                idxbuf[s * 32] = (live && r == P - 1) ? int(i) : -1;
             }
-            valid[s] = idx >= 0;
-            double2 v0 = make_double2(0.0, 0.0), v1 = make_double2(0.0, 0.0);
-            double e2 = 0.0;
-            if (valid[s]) {
-                const double2 *pp = reinterpret_cast<const double2 *>(a.pts + idx);
-                v0 = __ldg(pp);
-                v1 = __ldg(pp + 1);
-                if (a.eps2) e2 = __ldg(a.eps2 + idx);
-            }
-            // padded rows sit at a far-away sentinel: all their covariances are exactly 0
-            rx[s] = valid[s] ? T((v0.x - sx) * phi) : sentinel_coord<T>(r);
-            ry[s] = valid[s] ? T((v0.y - sy) * phi) : T(0);
-            rz[s] = valid[s] ? T((v1.x - sz) * phi) : T(0);
-            w[s] = valid[s] ? T(v1.y) : T(0);
-            dg[s] = valid[s] ? T(diag0 + e2) : T(1);
-            Pt pt;
-            pt.x = rx[s]; pt.y = ry[s];
-            if constexpr (DIM3) { pt.z = rz[s]; pt.pad = T(0); }
-            stage[r] = pt;
         }
-        __syncwarp();
-
-        // ---- stage 2: covariance build (lower triangle, row-owner layout) ----------------------
-        T A[R][P];
+    };
+    int nidx[R];
+    auto issue_rec = [&]() {  // idxbuf -> registers; records of those rows -> recbuf
 #pragma unroll
-        for (int j = 0; j < P - 1; ++j) {
-            const Pt cj = stage[j];
+        for (int s = 0; s < R; ++s) nidx[s] = idxbuf[s * 32];
+#pragma unroll
+        for (int s = 0; s < R; ++s) {
+            if (nidx[s] >= 0) {
+                const int slot = g * P + s * G + q;
+                const uint32_t dst = smem_addr(recbuf + (s * G + q) * 32);
+                const double4 *src = a.pts + nidx[s];
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst + 16u),
+                             "l"(reinterpret_cast<const char *>(src) + 16)
+                             : "memory");
+                if (DIM3 && a.eps2)
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_addr(e2buf + slot)),
+                                 "l"(a.eps2 + nidx[s])
+                                 : "memory");
+            }
+        }
+    };
+    issue_idx(grp0);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    issue_rec();
+    issue_idx(grp0 + gstride);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+
+    for (int64_t grp = grp0; grp < ngroups; grp += gstride) {
+        const int64_t i = a.lo + grp * W + g;
+        const bool live = i < a.hi;
+
+        // ---- consume the prefetched records ------------------------------------------------------
+        // Coordinates are re-centred on the location (row P-1) and scaled by phi in fp64 before any
+        // cast, so neighbour differences keep full relative accuracy (also in fp32 mode) and the
+        // covariance build works directly on u^2 = (phi*d)^2.
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncwarp();
+        T rx[R], ry[R], rz[R], w[R], dg[R];
+        bool valid[R];
+        {
+            const double2 *recs = reinterpret_cast<const double2 *>(recbuf);
+            const double2 self0 = recs[2 * (P - 1)];
+            const double sx = self0.x, sy = self0.y;
+            const double sz = DIM3 ? recs[2 * (P - 1) + 1].x : 0.0;
 #pragma unroll
             for (int s = 0; s < R; ++s) {
-                if (s * G + G - 1 > j) {
-                    const T dx = rx[s] - cj.x, dy = ry[s] - cj.y;
-                    T d2 = t_fma(dy, dy, t_fma(dx, dx, tiny_seed<T>()));
-                    if constexpr (DIM3) { const T dz = rz[s] - cj.z; d2 = t_fma(dz, dz, d2); }
-                    T v = cov_from_u<T, KERN>(fast_sqrt(d2), exp_tab, sigma2);
-                    if (j >= s * G) v = (s * G + q == j) ? dg[s] : v;  // diagonal block only
-                    A[s][j] = v;
+                const int r = s * G + q;
+                valid[s] = nidx[s] >= 0;
+                double2 v0 = make_double2(0.0, 0.0), v1 = make_double2(0.0, 0.0);
+                double e2 = 0.0;
+                if (valid[s]) {
+                    v0 = recs[2 * r];
+                    v1 = recs[2 * r + 1];
+                    if (!DIM3) e2 = v1.x;  // D < 3: the record's z slot carries eps2
+                    else if (a.eps2) e2 = e2buf[g * P + r];
+                }
+                // padded rows sit at a far-away sentinel: all their covariances are exactly 0
+                rx[s] = valid[s] ? T((v0.x - sx) * phi) : sentinel_coord<T>(r);
+                ry[s] = valid[s] ? T((v0.y - sy) * phi) : T(0);
+                rz[s] = valid[s] ? T((v1.x - sz) * phi) : T(0);
+                w[s] = valid[s] ? T(v1.y) : T(0);
+                dg[s] = valid[s] ? T(diag0 + e2) : T(1);
+                Pt pt;
+                pt.x = rx[s]; pt.y = ry[s];
+                if constexpr (DIM3) { pt.z = rz[s]; pt.pad = T(0); }
+                stage[r] = pt;
+            }
+        }
+        __syncwarp();  // recbuf fully read, stage[] fully written
+        issue_rec();                      // records of group t+1 (indices arrived an iteration ago)
+        issue_idx(grp + 2 * gstride);     // indices of group t+2
+        asm volatile("cp.async.commit_group;" ::: "memory");
+
+        // ---- stage 2: covariance build (lower triangle, row-owner layout) ----------------------
+        // CB pairs are evaluated in lock step and the results are parked in the lane's private column
+        // of the shared-memory tile: the build then keeps only O(CB) chains of temporaries live, so
+        // the instruction scheduler interleaves CB independent dependency chains (a single chain
+        // cannot fill the FP64 pipe: 8-cycle DFMA latency, 3 resident warps per scheduler).
+        constexpr int CB = 4;
+#pragma unroll
+        for (int s = 0; s < R; ++s) {
+#pragma unroll
+            for (int j0 = 0; j0 < P - 1; j0 += CB) {
+                if (j0 < s * G + G - 1) {  // row block s needs columns 0 .. s*G+G-2
+                    T d2[CB];
+#pragma unroll
+                    for (int b = 0; b < CB; ++b) {
+                        const int j = (j0 + b < P - 1) ? j0 + b : P - 2;
+                        const Pt cj = stage[j];
+                        const T dx = rx[s] - cj.x, dy = ry[s] - cj.y;
+                        d2[b] = t_fma(dy, dy, t_fma(dx, dx, tiny_seed<T>()));
+                        if constexpr (DIM3) { const T dz = rz[s] - cj.z; d2[b] = t_fma(dz, dz, d2[b]); }
+                    }
+                    cov_batch<KERN, CB>(d2, exp_tab, sigma2);
+#pragma unroll
+                    for (int b = 0; b < CB; ++b)
+                        if (j0 + b < s * G + G - 1) tile[(tile_offset<G>(s) + j0 + b) * 32] = d2[b];
                 }
             }
         }
-        // the last column of each diagonal block only carries lane G-1's diagonal entry
+        // the lane's rows come back from the tile into registers for the elimination
+        T A[R][P];
 #pragma unroll
-        for (int s = 0; s < R; ++s) A[s][s * G + G - 1] = dg[s];
-        __syncwarp();  // stage[] is rewritten by the next iteration
+        for (int s = 0; s < R; ++s) {
+#pragma unroll
+            for (int j = 0; j < P; ++j)
+                if (j < s * G + G - 1) {
+                    T v = tile[(tile_offset<G>(s) + j) * 32];
+                    if (j >= s * G) v = (s * G + q == j) ? dg[s] : v;  // diagonal block only
+                    A[s][j] = v;
+                }
+            A[s][s * G + G - 1] = dg[s];  // last column of the diagonal block: lane G-1's diagonal
+        }
 
         if (a.emit && live) {
             // per-location covariance blocks (the _CNs/_Ccross/_Cs accessors; parity output)
@@ -318,45 +482,50 @@ __global__ void __launch_bounds__(kThreads, MINB) fused_loglik_kernel(const Eval
 
         if (live && q == 0) {
             if (bad) {
-                acc_bad += 1u;
+                accbuf[64] += 1.0;
             } else {
-                acc_log += log(double(Flast));
-                acc_quad += double(rlast) * double(rlast) / double(Flast);
+                accbuf[0] += log(double(Flast));
+                accbuf[32] += double(rlast) * double(rlast) / double(Flast);
             }
         }
 
         if (a.emit) {
-            // b_i = L_N^{-T} ell, ell = last row of the unit-lower factor.  Rows travel through
-            // shared memory; one lane per location back-substitutes (parity / prediction output,
-            // not the metric's path).
-            T *dump = dump_all + (size_t(warp) * W + g) * P * P;
+            // b_i = L_N^{-T} ell, ell = last row of the unit-lower factor.  One location at a time:
+            // its G lanes dump their rows to shared memory and lane 0 back-substitutes (parity /
+            // prediction output, not the metric's path).
+            for (int gg = 0; gg < W; ++gg) {
+                if (g == gg) {
 #pragma unroll
-            for (int s = 0; s < R; ++s) {
-                const int r = s * G + q;
+                    for (int s = 0; s < R; ++s) {
+                        const int r = s * G + q;
 #pragma unroll
-                for (int kk = 0; kk < P; ++kk)
-                    if (kk < (s + 1) * G && kk < r) dump[r * P + kk] = A[s][kk];
-            }
-            __syncwarp();
-            if (live && q == 0) {
-                const int64_t o = i - a.lo;
-                if (a.F) a.F[o] = bad ? nan("") : double(Flast);
-                if (a.B) {
-                    double b[P];
-                    for (int kk = P - 2; kk >= 0; --kk) {
-                        double v = double(dump[(P - 1) * P + kk]);
-                        for (int r = kk + 1; r < P - 1; ++r) v -= double(dump[r * P + kk]) * b[r];
-                        b[kk] = v;
+                        for (int kk = 0; kk < P; ++kk)
+                            if (kk < (s + 1) * G && kk < r) dump[r * P + kk] = A[s][kk];
                     }
-                    for (int kk = 0; kk < m; ++kk) a.B[o * m + kk] = bad ? nan("") : b[kk];
                 }
+                __syncwarp();
+                if (g == gg && live && q == 0) {
+                    const int64_t o = i - a.lo;
+                    if (a.F) a.F[o] = bad ? nan("") : double(Flast);
+                    if (a.B) {
+                        double b[P];
+                        for (int kk = P - 2; kk >= 0; --kk) {
+                            double v = double(dump[(P - 1) * P + kk]);
+                            for (int r = kk + 1; r < P - 1; ++r) v -= double(dump[r * P + kk]) * b[r];
+                            b[kk] = v;
+                        }
+                        for (int kk = 0; kk < m; ++kk) a.B[o * m + kk] = bad ? nan("") : b[kk];
+                    }
+                }
+                __syncwarp();
             }
-            __syncwarp();
         }
     }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");  // drain copies issued for groups past the end
 
+    double acc_log = accbuf[0], acc_quad = accbuf[32];
     // ---- reduction: warp shuffle tree -> block -> per-block partial -> last block sums ------
-    double bad_d = double(acc_bad);
+    double bad_d = accbuf[64];
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) {
         acc_log += __shfl_xor_sync(0xffffffffu, acc_log, off);
@@ -387,7 +556,8 @@ __global__ void __launch_bounds__(kThreads, MINB) fused_loglik_kernel(const Eval
             t1 += __ldcg(part + size_t(b) * 3 + 1);
             t2 += __ldcg(part + size_t(b) * 3 + 2);
         }
-        __shared__ double fin[kThreads][3];
+        double(*fin)[3] = reinterpret_cast<double(*)[3]>(smem_raw);  // main-loop buffers are dead here
+        __syncthreads();
         fin[threadIdx.x][0] = t0; fin[threadIdx.x][1] = t1; fin[threadIdx.x][2] = t2;
         __syncthreads();
         for (int stride = kThreads / 2; stride > 0; stride >>= 1) {
@@ -443,9 +613,17 @@ int blocks_per_sm()
 template <typename T, int KERN>
 cudaError_t launch_family(int m, int D, const EvalArgs &a, int K, int grid_x, cudaStream_t stream)
 {
-    constexpr int MB4 = sizeof(T) == 8 ? 3 : 4;
+    // resident blocks per SM = register cap: fp64 runs best spill-free at 255 registers (8 warps/SM,
+    // ILP-4 covariance chains), see DESIGN.md tuning log
+    constexpr int MB4 = sizeof(T) == 8 ? 2 : 4;
     constexpr int MB16 = sizeof(T) == 8 ? 2 : 4;
 #define NNGP_CALL_LAUNCH(T_, G_, R_, K_, D3_, MB_) return launch_one<T_, G_, R_, K_, D3_, MB_>(a, K, grid_x, stream)
+#ifdef NNGP_TUNE  // development knob: resident blocks per SM (register cap) of the m <= 15 shape
+    if (const char *e = getenv("NNGP_TUNE_MINB"); e && m > 7 && m <= 15 && D != 3) {
+        if (atoi(e) == 3) return launch_one<T, 4, 4, KERN, false, 3>(a, K, grid_x, stream);
+        if (atoi(e) == 4) return launch_one<T, 4, 4, KERN, false, 4>(a, K, grid_x, stream);
+    }
+#endif
     if (D == 3) NNGP_DISPATCH_SHAPE(T, KERN, true, MB4, MB16, NNGP_CALL_LAUNCH);
     else NNGP_DISPATCH_SHAPE(T, KERN, false, MB4, MB16, NNGP_CALL_LAUNCH);
 #undef NNGP_CALL_LAUNCH
@@ -455,9 +633,15 @@ cudaError_t launch_family(int m, int D, const EvalArgs &a, int K, int grid_x, cu
 template <typename T, int KERN>
 int occupancy_family(int m, int D)
 {
-    constexpr int MB4 = sizeof(T) == 8 ? 3 : 4;
+    constexpr int MB4 = sizeof(T) == 8 ? 2 : 4;
     constexpr int MB16 = sizeof(T) == 8 ? 2 : 4;
 #define NNGP_CALL_OCC(T_, G_, R_, K_, D3_, MB_) return blocks_per_sm<T_, G_, R_, K_, D3_, MB_>()
+#ifdef NNGP_TUNE
+    if (const char *e = getenv("NNGP_TUNE_MINB"); e && m > 7 && m <= 15 && D != 3) {
+        if (atoi(e) == 3) return blocks_per_sm<T, 4, 4, KERN, false, 3>();
+        if (atoi(e) == 4) return blocks_per_sm<T, 4, 4, KERN, false, 4>();
+    }
+#endif
     if (D == 3) NNGP_DISPATCH_SHAPE(T, KERN, true, MB4, MB16, NNGP_CALL_OCC);
     else NNGP_DISPATCH_SHAPE(T, KERN, false, MB4, MB16, NNGP_CALL_OCC);
 #undef NNGP_CALL_OCC

@@ -190,11 +190,12 @@ int nngp_set_data(nngp_handle *h, const double *coords, int64_t n, int D, const 
     std::vector<double4> rec((size_t)n);
     for (int64_t i = 0; i < n; ++i) {
         const double *c = coords + i * D;
-        rec[(size_t)i] = make_double4(c[0], D > 1 ? c[1] : 0.0, D > 2 ? c[2] : 0.0, y[i]);
+        // D < 3: the unused z slot carries eps2 so the fused kernel gathers one record per neighbour
+        rec[(size_t)i] = make_double4(c[0], D > 1 ? c[1] : 0.0, D > 2 ? c[2] : (eps2 ? eps2[i] : 0.0), y[i]);
     }
     CUDA_TRY(h, cudaMalloc(&h->pts, sizeof(double4) * (size_t)n));
     CUDA_TRY(h, cudaMemcpyAsync(h->pts, rec.data(), sizeof(double4) * (size_t)n, cudaMemcpyHostToDevice, h->stream));
-    if (eps2) {
+    if (eps2 && D > 2) {
         CUDA_TRY(h, cudaMalloc(&h->eps2, sizeof(double) * (size_t)n));
         CUDA_TRY(h, cudaMemcpyAsync(h->eps2, eps2, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, h->stream));
     }

@@ -3,8 +3,9 @@
 // Data layout in HBM (per handle, one B200):
 //   pts   n x double4 {x, y, z, yval}   32-byte records: one L2 sector per neighbour gather,
 //                                       and a contiguous byte range per candidate tile for the
-//                                       k-NN's bulk (TMA 1-D) copies.  z = 0 when D < 3, y = 0 when D < 2.
-//   eps2  n x double (optional)         per-observation variance added to the diagonal.
+//                                       k-NN's bulk (TMA 1-D) copies.  z = eps2 (or 0) when D < 3, y = 0 when D < 2.
+//   eps2  n x double (optional, D = 3)  per-observation variance added to the diagonal; for D < 3 it
+//                                       rides in the record's unused z slot instead.
 //   nbr   n x m int32, row-major        neighbour table, -1 padded, valid entries first.
 // Coordinates and y are replicated on every GPU; a handle evaluates rows [lo, hi) only.
 #pragma once
