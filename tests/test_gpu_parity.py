@@ -304,3 +304,21 @@ def test_cfg3_full_size_properties():
     e.set_shard(lo, hi)
     st0 = orc.c_loglik(s, y, tab, 1, *P0[:3], lo=lo, hi=hi, threads=os.cpu_count() or 1)
     np.testing.assert_allclose(e.loglik(1, P0)[0][:2], st0[:2], rtol=RTOL64)
+
+
+def test_two_gpu_sharded_equals_single():
+    """NCCL path: skipped on a 1-GPU box; `gpurun --gpus 2` exercises it."""
+    import subprocess
+    import sys
+
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29631",
+                        os.path.join(root, "tools", "check_multi_gpu.py"), "cfg2"],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    assert "multi-gpu ok" in r.stdout
