@@ -52,6 +52,21 @@ __device__ __forceinline__ float t_fma(float a, float b, float c) { return fmaf(
 
 constexpr int kExpTab = 64;  // exp(t) = 2^k * 2^(j/64) * e^r,  |r| <= ln2/128
 
+// 64-bit constants of the covariance math.  Read as constant-bank operands (c[3][..]) they cost no
+// instruction; as literals ptxas re-materialises them (2 MOV each) inside the rolled build loop.
+__constant__ double kCovC[12] = {
+    0.375,                     // 0  sqrt correction
+    -92.33248261689366,        // 1  -64/ln2
+    6755399441055744.0,        // 2  1.5 * 2^52 (round-to-nearest magic)
+    -0.01083042469326756,      // 3  -(ln2/64) high part
+    -2.9815858269852933e-12,   // 4  -(ln2/64) low part
+    1.0 / 120.0,               // 5
+    1.0 / 24.0,                // 6
+    1.0 / 6.0,                 // 7
+    1.0 / 3.0,                 // 8  Matern 5/2
+    1e-290,                    // 9  tiny seed of the squared distance
+    0.0, 0.0};
+
 // u = sqrt(d2), d2 > 0 (the caller seeds the accumulation with a tiny positive constant).
 // One MUFU.RSQ64H seed and a third-order correction: rel. error ~ 2 ulp.
 __device__ __forceinline__ double fast_sqrt(double d2)
@@ -140,6 +155,7 @@ __device__ __forceinline__ void cov_batch(double (&x)[B], const double *tab, dou
 {
     double y0[B], t1[B], e[B], u[B], kd[B], r[B], qq[B], tv[B];
     int ki[B];
+    const double shift = kCovC[2], c5 = kCovC[5];  // second constants of two-constant FMAs: registers
 #pragma unroll
     for (int b = 0; b < B; ++b) asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y0[b]) : "d"(x[b]));
 #pragma unroll
@@ -147,25 +163,25 @@ __device__ __forceinline__ void cov_batch(double (&x)[B], const double *tab, dou
 #pragma unroll
     for (int b = 0; b < B; ++b) e[b] = fma(-t1[b], y0[b], 1.0);
 #pragma unroll
-    for (int b = 0; b < B; ++b) y0[b] = fma(e[b], 0.375, 0.5);
+    for (int b = 0; b < B; ++b) y0[b] = fma(e[b], kCovC[0], 0.5);
 #pragma unroll
     for (int b = 0; b < B; ++b) y0[b] = y0[b] * e[b];
 #pragma unroll
     for (int b = 0; b < B; ++b) u[b] = fma(t1[b], y0[b], t1[b]);
 #pragma unroll
-    for (int b = 0; b < B; ++b) kd[b] = fma(u[b], -92.33248261689366, 6755399441055744.0);
+    for (int b = 0; b < B; ++b) kd[b] = fma(u[b], kCovC[1], shift);
 #pragma unroll
-    for (int b = 0; b < B; ++b) { ki[b] = __double2loint(kd[b]); kd[b] = kd[b] - 6755399441055744.0; }
+    for (int b = 0; b < B; ++b) { ki[b] = __double2loint(kd[b]); kd[b] = kd[b] - shift; }
 #pragma unroll
     for (int b = 0; b < B; ++b) tv[b] = tab[ki[b] & (kExpTab - 1)];
 #pragma unroll
-    for (int b = 0; b < B; ++b) r[b] = fma(kd[b], -0.01083042469326756, -u[b]);
+    for (int b = 0; b < B; ++b) r[b] = fma(kd[b], kCovC[3], -u[b]);
 #pragma unroll
-    for (int b = 0; b < B; ++b) r[b] = fma(kd[b], -2.9815858269852933e-12, r[b]);
+    for (int b = 0; b < B; ++b) r[b] = fma(kd[b], kCovC[4], r[b]);
 #pragma unroll
-    for (int b = 0; b < B; ++b) qq[b] = fma(r[b], 1.0 / 120.0, 1.0 / 24.0);
+    for (int b = 0; b < B; ++b) qq[b] = fma(r[b], c5, kCovC[6]);
 #pragma unroll
-    for (int b = 0; b < B; ++b) qq[b] = fma(r[b], qq[b], 1.0 / 6.0);
+    for (int b = 0; b < B; ++b) qq[b] = fma(r[b], qq[b], kCovC[7]);
 #pragma unroll
     for (int b = 0; b < B; ++b) qq[b] = fma(r[b], qq[b], 0.5);
 #pragma unroll
@@ -184,7 +200,7 @@ __device__ __forceinline__ void cov_batch(double (&x)[B], const double *tab, dou
     for (int b = 0; b < B; ++b) {
         if (KERN == NNGP_EXPONENTIAL) x[b] = e[b];
         else if (KERN == NNGP_MATERN32) x[b] = fma(u[b], e[b], e[b]);
-        else x[b] = fma(u[b], fma(u[b], 1.0 / 3.0, 1.0), 1.0) * e[b];
+        else x[b] = fma(u[b], fma(u[b], kCovC[8], 1.0), 1.0) * e[b];
     }
 }
 template <int KERN, int B>
@@ -199,7 +215,7 @@ template <typename T> __device__ __forceinline__ T sentinel_coord(int r);
 template <> __device__ __forceinline__ double sentinel_coord<double>(int r) { return 1e100 * double(r + 1); }
 template <> __device__ __forceinline__ float sentinel_coord<float>(int r) { return 1e15f * float(r + 1); }
 template <typename T> __device__ __forceinline__ T tiny_seed();
-template <> __device__ __forceinline__ double tiny_seed<double>() { return 1e-290; }
+template <> __device__ __forceinline__ double tiny_seed<double>() { return kCovC[9]; }
 template <> __device__ __forceinline__ float tiny_seed<float>() { return 1e-36f; }
 
 __device__ __forceinline__ uint32_t smem_addr(const void *p)
@@ -213,11 +229,11 @@ __device__ __forceinline__ T grp_bcast(T v, int src)
     return __shfl_sync(0xffffffffu, v, src, G);
 }
 
-// entries of the strict lower triangle a lane parks: row block s holds columns 0 .. (s+1)*G-2
-template <int G, int R>
-__host__ __device__ constexpr int tile_entries() { return G * R * (R + 1) / 2 - R; }
-template <int G>
-__host__ __device__ constexpr int tile_offset(int s) { return G * s * (s + 1) / 2 - s; }
+// Shared-memory tile of one location: the strict lower triangle of the augmented matrix, row-major
+// (entry (a, b), a > b, at a(a-1)/2 + b).  The per-location stride is padded so the W locations of a
+// warp start 16 bytes (mod 128) apart: no systematic bank aliasing between the lane groups.
+template <int P>
+__host__ __device__ constexpr int tile_stride() { return (P * (P - 1) / 2 + 7) / 8 * 8 + 4; }
 
 // Per-warp shared-memory carve-up (bytes).  Everything a warp touches is private to it, so the
 // main loop needs __syncwarp only.
@@ -233,17 +249,21 @@ struct WarpSmem {
                                                                              // D < 3 records carry it in .z)
     static constexpr size_t idx = size_t(R) * 32 * sizeof(int);          // next group's neighbour indices
     static constexpr size_t acc = size_t(3) * 32 * sizeof(double);       // per-lane partial sums
-    static constexpr size_t tile = size_t(32) * tile_entries<G, R>() * sizeof(T);  // parked matrix rows
+    static constexpr size_t tile = (size_t(W) * tile_stride<P>() * sizeof(T) + 15) / 16 * 16;  // covariance entries
     static constexpr size_t stage = size_t(W) * stage_stride;                      // scaled coordinates
     static constexpr size_t dump = size_t(P) * P * sizeof(T);            // emit only: one location's factor
     __host__ __device__ static constexpr size_t total(bool emit) { return rec + e2 + idx + acc + tile + stage + (emit ? dump : 0); }
 };
 
+// block-shared part: exp table + the launch's pair list (one packed word per pair)
+template <int P>
+__host__ __device__ constexpr size_t block_smem() { return kExpTab * sizeof(double) + (size_t(P) * (P - 1) / 2 + 64) * 8; }
+
 // dynamic shared memory needed by one block
 template <typename T, int G, int R, bool DIM3>
 constexpr size_t smem_bytes(bool emit)
 {
-    return kExpTab * sizeof(double) + size_t(kWarps) * WarpSmem<T, G, R, DIM3>::total(emit);
+    return block_smem<G * R>() + size_t(kWarps) * WarpSmem<T, G, R, DIM3>::total(emit);
 }
 
 template <typename T, int G, int R, int KERN, bool DIM3, int MINB>
@@ -261,13 +281,14 @@ __global__ void __launch_bounds__(kThreads, MINB) fused_loglik_kernel(const Eval
     const int g = lane / G;  // location slot inside the warp
 
     T *exp_tab = reinterpret_cast<T *>(smem_raw);  // sigma2 * 2^(j/64) (fp64 path only)
-    unsigned char *wbase = smem_raw + kExpTab * sizeof(double) + size_t(warp) * WS::total(a.emit != 0);
+    uint2 *pair_lut = reinterpret_cast<uint2 *>(smem_raw + kExpTab * sizeof(double));
+    unsigned char *wbase = smem_raw + block_smem<P>() + size_t(warp) * WS::total(a.emit != 0);
     unsigned char *recbuf = wbase + g * WS::rec_stride;  // this location's records (16-byte aligned)
     double *e2buf = reinterpret_cast<double *>(wbase + WS::rec);
     int *idxbuf = reinterpret_cast<int *>(wbase + WS::rec + WS::e2) + lane;          // [s * 32]
     volatile double *accbuf = reinterpret_cast<volatile double *>(wbase + WS::rec + WS::e2 + WS::idx) + lane;
-    // lane-minor layout: entry e of this lane sits at tile[e * 32] -> conflict-free, no sync needed
-    volatile T *tile = reinterpret_cast<volatile T *>(wbase + WS::rec + WS::e2 + WS::idx + WS::acc) + lane;
+    T *tile_w = reinterpret_cast<T *>(wbase + WS::rec + WS::e2 + WS::idx + WS::acc);
+    T *tile = tile_w + g * tile_stride<P>();  // this location's covariance entries
     Pt *stage = reinterpret_cast<Pt *>(wbase + WS::rec + WS::e2 + WS::idx + WS::acc + WS::tile + g * WS::stage_stride);
     T *dump = reinterpret_cast<T *>(wbase + WS::rec + WS::e2 + WS::idx + WS::acc + WS::tile + WS::stage);
 
@@ -278,7 +299,28 @@ __global__ void __launch_bounds__(kThreads, MINB) fused_loglik_kernel(const Eval
     const int m = a.m;
     if (threadIdx.x < kExpTab) exp_tab[threadIdx.x] = T(prm[0] * exp2(double(threadIdx.x) / kExpTab));
     accbuf[0] = 0.0; accbuf[32] = 0.0; accbuf[64] = 0.0;  // sum log F, sum r^2/F, n_bad: rarely touched,
-    __syncthreads();                                        // kept out of the register file
+                                                            // kept out of the register file
+    // The launch's pair list: rows in play are the m neighbour rows and the location's own row P-1
+    // (rows m .. P-2 are identity padding: their entries stay at the zero the tile is filled with).
+    // Pair t -> packed {row a, column b, tile offset a(a-1)/2 + b}; lanes walk the list with stride G,
+    // which splits the build evenly (m = 15: 30 pairs per lane) whatever the row-owner layout is.
+    constexpr int CB = 4;  // pairs evaluated in lock step by one lane
+    const int rows_in_play = m + 1;
+    const int npairs = rows_in_play * (rows_in_play - 1) / 2;
+    const int nbatch = (npairs + G * CB - 1) / (G * CB);  // build-loop trips; the list is padded to it
+    for (int t = threadIdx.x; t < nbatch * G * CB; t += kThreads) {
+        const int tt = t < npairs ? t : npairs - 1;  // padding repeats the last pair (same value, same slot)
+        int ia = int((1.0f + sqrtf(1.0f + 8.0f * float(tt))) * 0.5f);
+        while (ia * (ia - 1) / 2 > tt) --ia;
+        while ((ia + 1) * ia / 2 <= tt) ++ia;
+        const int ib = tt - ia * (ia - 1) / 2;
+        const int ra = (ia == rows_in_play - 1) ? P - 1 : ia;
+        // byte offsets: row point | column point << 16 inside stage[], entry inside the tile
+        pair_lut[t] = make_uint2(uint32_t(ra * sizeof(Pt)) | (uint32_t(ib * sizeof(Pt)) << 16),
+                                 uint32_t((ra * (ra - 1) / 2 + ib) * sizeof(T)));
+    }
+    for (int k = lane; k < W * tile_stride<P>(); k += 32) tile_w[k] = T(0);
+    __syncthreads();
 
     const int64_t nloc = a.hi - a.lo;
     const int64_t ngroups = (nloc + W - 1) / W;
@@ -379,46 +421,58 @@ __global__ void __launch_bounds__(kThreads, MINB) fused_loglik_kernel(const Eval
         issue_idx(grp + 2 * gstride);     // indices of group t+2
         asm volatile("cp.async.commit_group;" ::: "memory");
 
-        // ---- stage 2: covariance build (lower triangle, row-owner layout) ----------------------
-        // CB pairs are evaluated in lock step and the results are parked in the lane's private column
-        // of the shared-memory tile: the build then keeps only O(CB) chains of temporaries live, so
-        // the instruction scheduler interleaves CB independent dependency chains (a single chain
-        // cannot fill the FP64 pipe: 8-cycle DFMA latency, 3 resident warps per scheduler).
-        constexpr int CB = 4;
+        // ---- stage 2: covariance build ------------------------------------------------------------
+        // A rolled loop over this lane's share of the pair list, CB pairs in lock step (independent
+        // dependency chains: one chain cannot fill the FP64 pipe -- 8-cycle DFMA latency).  Operands
+        // come from the staged coordinates, results go to the location's tile: nothing here needs a
+        // register index, so the loop body stays small (instruction cache) and holds few registers.
+        {
+            // the list pointer is rebuilt from %laneid here on purpose: as an ordinary loop-carried value
+            // ptxas spills it across the elimination and its local-memory reload stalled every
+            // iteration (10 % of the kernel in the ncu source view)
+            uint32_t lane_now;
+            asm volatile("mov.u32 %0, %%laneid;" : "=r"(lane_now));
+            const uint2 *lp = pair_lut + (lane_now % G);
+            const unsigned char *sb = reinterpret_cast<const unsigned char *>(stage);
+            unsigned char *tb = reinterpret_cast<unsigned char *>(tile);
+#pragma unroll 1
+            for (int u = 0; u < nbatch; ++u, lp += G * CB) {
+                T d2[CB];
+                uint32_t eoff[CB];
 #pragma unroll
-        for (int s = 0; s < R; ++s) {
-#pragma unroll
-            for (int j0 = 0; j0 < P - 1; j0 += CB) {
-                if (j0 < s * G + G - 1) {  // row block s needs columns 0 .. s*G+G-2
-                    T d2[CB];
-#pragma unroll
-                    for (int b = 0; b < CB; ++b) {
-                        const int j = (j0 + b < P - 1) ? j0 + b : P - 2;
-                        const Pt cj = stage[j];
-                        const T dx = rx[s] - cj.x, dy = ry[s] - cj.y;
-                        d2[b] = t_fma(dy, dy, t_fma(dx, dx, tiny_seed<T>()));
-                        if constexpr (DIM3) { const T dz = rz[s] - cj.z; d2[b] = t_fma(dz, dz, d2[b]); }
-                    }
-                    cov_batch<KERN, CB>(d2, exp_tab, sigma2);
-#pragma unroll
-                    for (int b = 0; b < CB; ++b)
-                        if (j0 + b < s * G + G - 1) tile[(tile_offset<G>(s) + j0 + b) * 32] = d2[b];
+                for (int b = 0; b < CB; ++b) {
+                    const uint2 pw = lp[b * G];
+                    const Pt pa = *reinterpret_cast<const Pt *>(sb + (pw.x & 0xffffu));
+                    const Pt pb = *reinterpret_cast<const Pt *>(sb + (pw.x >> 16));
+                    eoff[b] = pw.y;
+                    const T dx = pa.x - pb.x, dy = pa.y - pb.y;
+                    d2[b] = t_fma(dy, dy, t_fma(dx, dx, tiny_seed<T>()));
+                    if constexpr (DIM3) { const T dz = pa.z - pb.z; d2[b] = t_fma(dz, dz, d2[b]); }
                 }
+                cov_batch<KERN, CB>(d2, exp_tab, sigma2);
+#pragma unroll
+                for (int b = 0; b < CB; ++b) *reinterpret_cast<T *>(tb + eoff[b]) = d2[b];
             }
         }
-        // the lane's rows come back from the tile into registers for the elimination
+        __syncwarp();  // the tile is complete: lanes now read entries other lanes of the group built
+
+        // the lane's rows come from the tile into registers for the elimination
         T A[R][P];
 #pragma unroll
         for (int s = 0; s < R; ++s) {
+            const int r = s * G + q;
+            const T *row = tile + r * (r - 1) / 2;
 #pragma unroll
             for (int j = 0; j < P; ++j)
                 if (j < s * G + G - 1) {
-                    T v = tile[(tile_offset<G>(s) + j) * 32];
-                    if (j >= s * G) v = (s * G + q == j) ? dg[s] : v;  // diagonal block only
+                    T v = T(0);
+                    if (j < r) v = row[j];
+                    if (j >= s * G) v = (r == j) ? dg[s] : v;  // diagonal block only
                     A[s][j] = v;
                 }
             A[s][s * G + G - 1] = dg[s];  // last column of the diagonal block: lane G-1's diagonal
         }
+        __syncwarp();  // tile and stage[] are rewritten by the next iteration
 
         if (a.emit && live) {
             // per-location covariance blocks (the _CNs/_Ccross/_Cs accessors; parity output)
@@ -601,12 +655,12 @@ int blocks_per_sm()
 }
 
 // row-count variants: (G, R) -> P = G*R >= m + 1
-//   m <= 7 : (4, 2)   m <= 15 : (4, 4)   m <= 31 : (16, 2)   m == 32 : (16, 3)
+//   m <= 7 : (4, 2)   m <= 15 : (4, 4)   m <= 31 : (8, 4)   m == 32 : (16, 3)
 #define NNGP_DISPATCH_SHAPE(T, KERN, DIM3, MINB4, MINB16, CALL)                   \
     do {                                                                          \
         if (m <= 7) { CALL(T, 4, 2, KERN, DIM3, MINB4); }                         \
         else if (m <= 15) { CALL(T, 4, 4, KERN, DIM3, MINB4); }                   \
-        else if (m <= 31) { CALL(T, 16, 2, KERN, DIM3, MINB16); }                 \
+        else if (m <= 31) { CALL(T, 8, 4, KERN, DIM3, MINB16); }                  \
         else { CALL(T, 16, 3, KERN, DIM3, MINB16); }                              \
     } while (0)
 
@@ -648,7 +702,7 @@ int occupancy_family(int m, int D)
     return 1;
 }
 
-inline int locations_per_warp(int m) { return m <= 15 ? 8 : 2; }
+inline int locations_per_warp(int m) { return m <= 15 ? 8 : (m <= 31 ? 4 : 2); }
 
 }  // namespace nngp_fused
 

@@ -47,7 +47,7 @@ void free_dev(P *&p)
     p = nullptr;
 }
 
-int locations_per_warp(int m) { return m <= 15 ? 8 : 2; }
+int locations_per_warp(int m) { return m <= 15 ? 8 : (m <= 31 ? 4 : 2); }
 
 int family_occupancy(int dtype, int kernel_id, int m, int D)
 {
