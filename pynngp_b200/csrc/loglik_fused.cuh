@@ -23,6 +23,7 @@
 #pragma once
 #include <math.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include "nngp_common.cuh"
 
@@ -237,7 +238,7 @@ __host__ __device__ constexpr int tile_stride() { return (P * (P - 1) / 2 + 7) /
 
 // Per-warp shared-memory carve-up (bytes).  Everything a warp touches is private to it, so the
 // main loop needs __syncwarp only.
-template <typename T, int G, int R, bool DIM3>
+template <typename T, int G, int R, bool DIM3, bool ROLLED>
 struct WarpSmem {
     static constexpr int P = G * R, W = 32 / G;
     // location strides are padded by 16 bytes so the W groups of a warp start in different banks
@@ -249,30 +250,30 @@ struct WarpSmem {
                                                                              // D < 3 records carry it in .z)
     static constexpr size_t idx = size_t(R) * 32 * sizeof(int);          // next group's neighbour indices
     static constexpr size_t acc = size_t(3) * 32 * sizeof(double);       // per-lane partial sums
-    static constexpr size_t tile = (size_t(W) * tile_stride<P>() * sizeof(T) + 15) / 16 * 16;  // covariance entries
+    static constexpr size_t tile = ROLLED ? (size_t(W) * tile_stride<P>() * sizeof(T) + 15) / 16 * 16 : 0;  // covariance entries
     static constexpr size_t stage = size_t(W) * stage_stride;                      // scaled coordinates
     static constexpr size_t dump = size_t(P) * P * sizeof(T);            // emit only: one location's factor
     __host__ __device__ static constexpr size_t total(bool emit) { return rec + e2 + idx + acc + tile + stage + (emit ? dump : 0); }
 };
 
 // block-shared part: exp table + the launch's pair list (one packed word per pair)
-template <int P>
-__host__ __device__ constexpr size_t block_smem() { return kExpTab * sizeof(double) + (size_t(P) * (P - 1) / 2 + 64) * 8; }
+template <int P, bool ROLLED>
+__host__ __device__ constexpr size_t block_smem() { return kExpTab * sizeof(double) + (ROLLED ? (size_t(P) * (P - 1) / 2 + 64) * 8 : 0); }
 
 // dynamic shared memory needed by one block
-template <typename T, int G, int R, bool DIM3>
+template <typename T, int G, int R, bool DIM3, bool ROLLED>
 constexpr size_t smem_bytes(bool emit)
 {
-    return block_smem<G * R>() + size_t(kWarps) * WarpSmem<T, G, R, DIM3>::total(emit);
+    return block_smem<G * R, ROLLED>() + size_t(kWarps) * WarpSmem<T, G, R, DIM3, ROLLED>::total(emit);
 }
 
-template <typename T, int G, int R, int KERN, bool DIM3, int MINB>
+template <typename T, int G, int R, int KERN, bool DIM3, int MINB, bool ROLLED>
 __global__ void __launch_bounds__(kThreads, MINB) fused_loglik_kernel(const EvalArgs a)
 {
     constexpr int P = G * R;   // rows of the augmented matrix
     constexpr int W = 32 / G;  // locations per warp
     using Pt = StagePt<T, DIM3>;
-    using WS = WarpSmem<T, G, R, DIM3>;
+    using WS = WarpSmem<T, G, R, DIM3, ROLLED>;
 
     extern __shared__ __align__(32) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31;
@@ -282,7 +283,7 @@ __global__ void __launch_bounds__(kThreads, MINB) fused_loglik_kernel(const Eval
 
     T *exp_tab = reinterpret_cast<T *>(smem_raw);  // sigma2 * 2^(j/64) (fp64 path only)
     uint2 *pair_lut = reinterpret_cast<uint2 *>(smem_raw + kExpTab * sizeof(double));
-    unsigned char *wbase = smem_raw + block_smem<P>() + size_t(warp) * WS::total(a.emit != 0);
+    unsigned char *wbase = smem_raw + block_smem<P, ROLLED>() + size_t(warp) * WS::total(a.emit != 0);
     unsigned char *recbuf = wbase + g * WS::rec_stride;  // this location's records (16-byte aligned)
     double *e2buf = reinterpret_cast<double *>(wbase + WS::rec);
     int *idxbuf = reinterpret_cast<int *>(wbase + WS::rec + WS::e2) + lane;          // [s * 32]
@@ -308,18 +309,20 @@ __global__ void __launch_bounds__(kThreads, MINB) fused_loglik_kernel(const Eval
     const int rows_in_play = m + 1;
     const int npairs = rows_in_play * (rows_in_play - 1) / 2;
     const int nbatch = (npairs + G * CB - 1) / (G * CB);  // build-loop trips; the list is padded to it
-    for (int t = threadIdx.x; t < nbatch * G * CB; t += kThreads) {
-        const int tt = t < npairs ? t : npairs - 1;  // padding repeats the last pair (same value, same slot)
-        int ia = int((1.0f + sqrtf(1.0f + 8.0f * float(tt))) * 0.5f);
-        while (ia * (ia - 1) / 2 > tt) --ia;
-        while ((ia + 1) * ia / 2 <= tt) ++ia;
-        const int ib = tt - ia * (ia - 1) / 2;
-        const int ra = (ia == rows_in_play - 1) ? P - 1 : ia;
-        // byte offsets: row point | column point << 16 inside stage[], entry inside the tile
-        pair_lut[t] = make_uint2(uint32_t(ra * sizeof(Pt)) | (uint32_t(ib * sizeof(Pt)) << 16),
-                                 uint32_t((ra * (ra - 1) / 2 + ib) * sizeof(T)));
+    if (ROLLED) {
+        for (int t = threadIdx.x; t < nbatch * G * CB; t += kThreads) {
+            const int tt = t < npairs ? t : npairs - 1;  // padding repeats the last pair (same value, same slot)
+            int ia = int((1.0f + sqrtf(1.0f + 8.0f * float(tt))) * 0.5f);
+            while (ia * (ia - 1) / 2 > tt) --ia;
+            while ((ia + 1) * ia / 2 <= tt) ++ia;
+            const int ib = tt - ia * (ia - 1) / 2;
+            const int ra = (ia == rows_in_play - 1) ? P - 1 : ia;
+            // byte offsets: row point | column point << 16 inside stage[], entry inside the tile
+            pair_lut[t] = make_uint2(uint32_t(ra * sizeof(Pt)) | (uint32_t(ib * sizeof(Pt)) << 16),
+                                     uint32_t((ra * (ra - 1) / 2 + ib) * sizeof(T)));
+        }
+        for (int k = lane; k < W * tile_stride<P>(); k += 32) tile_w[k] = T(0);
     }
-    for (int k = lane; k < W * tile_stride<P>(); k += 32) tile_w[k] = T(0);
     __syncthreads();
 
     const int64_t nloc = a.hi - a.lo;
@@ -422,55 +425,92 @@ __global__ void __launch_bounds__(kThreads, MINB) fused_loglik_kernel(const Eval
         asm volatile("cp.async.commit_group;" ::: "memory");
 
         // ---- stage 2: covariance build ------------------------------------------------------------
+        T A[R][P];
+        if constexpr (ROLLED) {
         // A rolled loop over this lane's share of the pair list, CB pairs in lock step (independent
         // dependency chains: one chain cannot fill the FP64 pipe -- 8-cycle DFMA latency).  Operands
         // come from the staged coordinates, results go to the location's tile: nothing here needs a
         // register index, so the loop body stays small (instruction cache) and holds few registers.
-        {
-            // the list pointer is rebuilt from %laneid here on purpose: as an ordinary loop-carried value
-            // ptxas spills it across the elimination and its local-memory reload stalled every
-            // iteration (10 % of the kernel in the ncu source view)
-            uint32_t lane_now;
-            asm volatile("mov.u32 %0, %%laneid;" : "=r"(lane_now));
-            const uint2 *lp = pair_lut + (lane_now % G);
-            const unsigned char *sb = reinterpret_cast<const unsigned char *>(stage);
-            unsigned char *tb = reinterpret_cast<unsigned char *>(tile);
-#pragma unroll 1
-            for (int u = 0; u < nbatch; ++u, lp += G * CB) {
-                T d2[CB];
-                uint32_t eoff[CB];
-#pragma unroll
-                for (int b = 0; b < CB; ++b) {
-                    const uint2 pw = lp[b * G];
-                    const Pt pa = *reinterpret_cast<const Pt *>(sb + (pw.x & 0xffffu));
-                    const Pt pb = *reinterpret_cast<const Pt *>(sb + (pw.x >> 16));
-                    eoff[b] = pw.y;
-                    const T dx = pa.x - pb.x, dy = pa.y - pb.y;
-                    d2[b] = t_fma(dy, dy, t_fma(dx, dx, tiny_seed<T>()));
-                    if constexpr (DIM3) { const T dz = pa.z - pb.z; d2[b] = t_fma(dz, dz, d2[b]); }
+            {
+                // the list pointer is rebuilt from %laneid here on purpose: as an ordinary loop-carried value
+                // ptxas spills it across the elimination and its local-memory reload stalled every
+                // iteration (10 % of the kernel in the ncu source view)
+                uint32_t lane_now;
+                asm volatile("mov.u32 %0, %%laneid;" : "=r"(lane_now));
+                const uint2 *lp = pair_lut + (lane_now % G);
+                const unsigned char *sb = reinterpret_cast<const unsigned char *>(stage);
+                unsigned char *tb = reinterpret_cast<unsigned char *>(tile);
+    #pragma unroll 1
+                for (int u = 0; u < nbatch; ++u, lp += G * CB) {
+                    T d2[CB];
+                    uint32_t eoff[CB];
+    #pragma unroll
+                    for (int b = 0; b < CB; ++b) {
+                        const uint2 pw = lp[b * G];
+                        const Pt pa = *reinterpret_cast<const Pt *>(sb + (pw.x & 0xffffu));
+                        const Pt pb = *reinterpret_cast<const Pt *>(sb + (pw.x >> 16));
+                        eoff[b] = pw.y;
+                        const T dx = pa.x - pb.x, dy = pa.y - pb.y;
+                        d2[b] = t_fma(dy, dy, t_fma(dx, dx, tiny_seed<T>()));
+                        if constexpr (DIM3) { const T dz = pa.z - pb.z; d2[b] = t_fma(dz, dz, d2[b]); }
+                    }
+                    cov_batch<KERN, CB>(d2, exp_tab, sigma2);
+    #pragma unroll
+                    for (int b = 0; b < CB; ++b) *reinterpret_cast<T *>(tb + eoff[b]) = d2[b];
                 }
-                cov_batch<KERN, CB>(d2, exp_tab, sigma2);
-#pragma unroll
-                for (int b = 0; b < CB; ++b) *reinterpret_cast<T *>(tb + eoff[b]) = d2[b];
             }
-        }
-        __syncwarp();  // the tile is complete: lanes now read entries other lanes of the group built
+            __syncwarp();  // the tile is complete: lanes now read entries other lanes of the group built
 
-        // the lane's rows come from the tile into registers for the elimination
-        T A[R][P];
+            // the lane's rows come from the tile into registers for the elimination
+    #pragma unroll
+            for (int s = 0; s < R; ++s) {
+                const int r = s * G + q;
+                const T *row = tile + r * (r - 1) / 2;
+    #pragma unroll
+                for (int j = 0; j < P; ++j)
+                    if (j < s * G + G - 1) {
+                        T v = T(0);
+                        if (j < r) v = row[j];
+                        if (j >= s * G) v = (r == j) ? dg[s] : v;  // diagonal block only
+                        A[s][j] = v;
+                    }
+                A[s][s * G + G - 1] = dg[s];  // last column of the diagonal block: lane G-1's diagonal
+            }
+        } else {
+            // Row-owner build, fully unrolled: for column j the lane evaluates the pairs (row, j) of up
+            // to CB of its rows in lock step (independent chains sharing one column point) and the
+            // results go straight to the row registers.  Used where the rows-per-lane count makes this
+            // layout nearly balanced (G = 2) and the shuffle / shared-memory pipe is the scarcer unit.
+            constexpr int CB = 4;
 #pragma unroll
-        for (int s = 0; s < R; ++s) {
-            const int r = s * G + q;
-            const T *row = tile + r * (r - 1) / 2;
+            for (int j = 0; j < P - 1; ++j) {
+                const Pt cj = stage[j];
 #pragma unroll
-            for (int j = 0; j < P; ++j)
-                if (j < s * G + G - 1) {
-                    T v = T(0);
-                    if (j < r) v = row[j];
-                    if (j >= s * G) v = (r == j) ? dg[s] : v;  // diagonal block only
-                    A[s][j] = v;
+                for (int s0 = 0; s0 < R; s0 += CB) {
+                    if ((((s0 + CB < R) ? s0 + CB : R) - 1) * G + G - 1 > j) {
+                        T d2[CB];
+#pragma unroll
+                        for (int b = 0; b < CB; ++b) {
+                            const int s = (s0 + b < R) ? s0 + b : R - 1;
+                            const T dx = rx[s] - cj.x, dy = ry[s] - cj.y;
+                            d2[b] = t_fma(dy, dy, t_fma(dx, dx, tiny_seed<T>()));
+                            if constexpr (DIM3) { const T dz = rz[s] - cj.z; d2[b] = t_fma(dz, dz, d2[b]); }
+                        }
+                        cov_batch<KERN, CB>(d2, exp_tab, sigma2);
+#pragma unroll
+                        for (int b = 0; b < CB; ++b) {
+                            const int s = s0 + b;
+                            if (s < R && s * G + G - 1 > j) {
+                                T v = d2[b];
+                                if (j >= s * G) v = (s * G + q == j) ? dg[s] : v;  // diagonal block only
+                                A[s][j] = v;
+                            }
+                        }
+                    }
                 }
-            A[s][s * G + G - 1] = dg[s];  // last column of the diagonal block: lane G-1's diagonal
+            }
+#pragma unroll
+            for (int s = 0; s < R; ++s) A[s][s * G + G - 1] = dg[s];
         }
         __syncwarp();  // tile and stage[] are rewritten by the next iteration
 
@@ -632,77 +672,84 @@ __global__ void __launch_bounds__(kThreads, MINB) fused_loglik_kernel(const Eval
 }
 
 // ---- host-side dispatch of one (T, KERN) family -------------------------------------------------
-template <typename T, int G, int R, int KERN, bool DIM3, int MINB>
+template <typename T, int G, int R, int KERN, bool DIM3, int MINB, bool ROLLED>
 cudaError_t launch_one(const EvalArgs &a, int K, int grid_x, cudaStream_t stream)
 {
-    auto kern = fused_loglik_kernel<T, G, R, KERN, DIM3, MINB>;
-    const size_t smem = smem_bytes<T, G, R, DIM3>(a.emit != 0);
+    auto kern = fused_loglik_kernel<T, G, R, KERN, DIM3, MINB, ROLLED>;
+    const size_t smem = smem_bytes<T, G, R, DIM3, ROLLED>(a.emit != 0);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     kern<<<dim3(grid_x, K, 1), kThreads, smem, stream>>>(a);
     return cudaGetLastError();
 }
 
-template <typename T, int G, int R, int KERN, bool DIM3, int MINB>
+template <typename T, int G, int R, int KERN, bool DIM3, int MINB, bool ROLLED>
 int blocks_per_sm()
 {
-    auto kern = fused_loglik_kernel<T, G, R, KERN, DIM3, MINB>;
+    auto kern = fused_loglik_kernel<T, G, R, KERN, DIM3, MINB, ROLLED>;
     int nb = 0;
-    const size_t smem = smem_bytes<T, G, R, DIM3>(false);
+    const size_t smem = smem_bytes<T, G, R, DIM3, ROLLED>(false);
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, kThreads, smem) != cudaSuccess) nb = 1;
     return nb < 1 ? 1 : nb;
 }
 
-// row-count variants: (G, R) -> P = G*R >= m + 1
-//   m <= 7 : (4, 2)   m <= 15 : (4, 4)   m <= 31 : (8, 4)   m == 32 : (16, 3)
-#define NNGP_DISPATCH_SHAPE(T, KERN, DIM3, MINB4, MINB16, CALL)                   \
-    do {                                                                          \
-        if (m <= 7) { CALL(T, 4, 2, KERN, DIM3, MINB4); }                         \
-        else if (m <= 15) { CALL(T, 4, 4, KERN, DIM3, MINB4); }                   \
-        else if (m <= 31) { CALL(T, 8, 4, KERN, DIM3, MINB16); }                  \
-        else { CALL(T, 16, 3, KERN, DIM3, MINB16); }                              \
-    } while (0)
+// ---- shape table: (G lanes per location, R rows per lane) -> P = G*R >= m + 1 rows --------------------
+//   m <=  7 : (4, 2) unrolled row-owner build
+//   m <= 15 : (4, 4) unrolled row-owner build (fp64: 168 registers, 12 warps/SM)
+//   m <= 31 : (8, 4) rolled pair-list build
+//   m == 32 : (16, 3) rolled pair-list build
+// MINB = resident blocks per SM the kernel is compiled for (the register cap).
+struct ShapeInfo {
+    int blocks_per_sm;
+    int loc_per_warp;
+};
+
+template <typename T, int KERN>
+struct Launcher {
+    const EvalArgs &a;
+    int K, grid_x;
+    cudaStream_t stream;
+    template <int G, int R, bool DIM3, int MINB, bool ROLLED>
+    cudaError_t run() const { return launch_one<T, G, R, KERN, DIM3, MINB, ROLLED>(a, K, grid_x, stream); }
+};
+template <typename T, int KERN>
+struct Describer {
+    template <int G, int R, bool DIM3, int MINB, bool ROLLED>
+    ShapeInfo run() const { return ShapeInfo{blocks_per_sm<T, G, R, KERN, DIM3, MINB, ROLLED>(), 32 / G}; }
+};
+
+template <typename T, bool DIM3, typename F>
+auto dispatch_shape(int m, const F &f)
+{
+    constexpr bool F64 = sizeof(T) == 8;
+#ifdef NNGP_TUNE  // development knob for the m <= 15 shape: NNGP_TUNE_SHAPE = 4x4r | 4x4u | 4x4u3 | 2x8u
+    if (const char *e = getenv("NNGP_TUNE_SHAPE"); e && m > 7 && m <= 15 && !DIM3) {
+        if (!strcmp(e, "4x4r")) return f.template run<4, 4, DIM3, 2, true>();
+        if (!strcmp(e, "4x4u")) return f.template run<4, 4, DIM3, 2, false>();
+        if (!strcmp(e, "4x4u3")) return f.template run<4, 4, DIM3, 3, false>();
+        if (!strcmp(e, "2x8u")) return f.template run<2, 8, DIM3, 2, false>();
+    }
+#endif
+    if (m <= 7) return f.template run<4, 2, DIM3, 4, false>();
+    if (m <= 15) return f.template run<4, 4, DIM3, (F64 ? 3 : 4), false>();
+    if (m <= 31) return f.template run<8, 4, DIM3, (F64 ? 2 : 4), true>();
+    return f.template run<16, 3, DIM3, (F64 ? 2 : 4), true>();
+}
 
 template <typename T, int KERN>
 cudaError_t launch_family(int m, int D, const EvalArgs &a, int K, int grid_x, cudaStream_t stream)
 {
-    // resident blocks per SM = register cap: fp64 runs best spill-free at 255 registers (8 warps/SM,
-    // ILP-4 covariance chains), see DESIGN.md tuning log
-    constexpr int MB4 = sizeof(T) == 8 ? 2 : 4;
-    constexpr int MB16 = sizeof(T) == 8 ? 2 : 4;
-#define NNGP_CALL_LAUNCH(T_, G_, R_, K_, D3_, MB_) return launch_one<T_, G_, R_, K_, D3_, MB_>(a, K, grid_x, stream)
-#ifdef NNGP_TUNE  // development knob: resident blocks per SM (register cap) of the m <= 15 shape
-    if (const char *e = getenv("NNGP_TUNE_MINB"); e && m > 7 && m <= 15 && D != 3) {
-        if (atoi(e) == 3) return launch_one<T, 4, 4, KERN, false, 3>(a, K, grid_x, stream);
-        if (atoi(e) == 4) return launch_one<T, 4, 4, KERN, false, 4>(a, K, grid_x, stream);
-    }
-#endif
-    if (D == 3) NNGP_DISPATCH_SHAPE(T, KERN, true, MB4, MB16, NNGP_CALL_LAUNCH);
-    else NNGP_DISPATCH_SHAPE(T, KERN, false, MB4, MB16, NNGP_CALL_LAUNCH);
-#undef NNGP_CALL_LAUNCH
-    return cudaErrorInvalidValue;
+    const Launcher<T, KERN> f{a, K, grid_x, stream};
+    return D == 3 ? dispatch_shape<T, true>(m, f) : dispatch_shape<T, false>(m, f);
 }
 
 template <typename T, int KERN>
-int occupancy_family(int m, int D)
+ShapeInfo shape_family(int m, int D)
 {
-    constexpr int MB4 = sizeof(T) == 8 ? 2 : 4;
-    constexpr int MB16 = sizeof(T) == 8 ? 2 : 4;
-#define NNGP_CALL_OCC(T_, G_, R_, K_, D3_, MB_) return blocks_per_sm<T_, G_, R_, K_, D3_, MB_>()
-#ifdef NNGP_TUNE
-    if (const char *e = getenv("NNGP_TUNE_MINB"); e && m > 7 && m <= 15 && D != 3) {
-        if (atoi(e) == 3) return blocks_per_sm<T, 4, 4, KERN, false, 3>();
-        if (atoi(e) == 4) return blocks_per_sm<T, 4, 4, KERN, false, 4>();
-    }
-#endif
-    if (D == 3) NNGP_DISPATCH_SHAPE(T, KERN, true, MB4, MB16, NNGP_CALL_OCC);
-    else NNGP_DISPATCH_SHAPE(T, KERN, false, MB4, MB16, NNGP_CALL_OCC);
-#undef NNGP_CALL_OCC
-    return 1;
+    const Describer<T, KERN> f{};
+    return D == 3 ? dispatch_shape<T, true>(m, f) : dispatch_shape<T, false>(m, f);
 }
-
-inline int locations_per_warp(int m) { return m <= 15 ? 8 : (m <= 31 ? 4 : 2); }
 
 }  // namespace nngp_fused
 
@@ -713,4 +760,9 @@ inline int locations_per_warp(int m) { return m <= 15 ? 8 : (m <= 31 ? 4 : 2); }
     {                                                                                             \
         return nngp_fused::launch_family<T, KERN>(m, D, a, K, grid_x, stream);                    \
     }                                                                                             \
-    int nngp_occupancy_##NAME(int m, int D) { return nngp_fused::occupancy_family<T, KERN>(m, D); }
+    void nngp_shape_##NAME(int m, int D, int *blocks_per_sm, int *loc_per_warp)                   \
+    {                                                                                             \
+        const nngp_fused::ShapeInfo si = nngp_fused::shape_family<T, KERN>(m, D);                 \
+        *blocks_per_sm = si.blocks_per_sm;                                                        \
+        *loc_per_warp = si.loc_per_warp;                                                          \
+    }

@@ -11,7 +11,7 @@
 #define NNGP_DECLARE_FAMILY(NAME)                                                                \
     cudaError_t nngp_launch_##NAME(int m, int D, const EvalArgs &a, int K, int grid_x,           \
                                    cudaStream_t stream);                                         \
-    int nngp_occupancy_##NAME(int m, int D);
+    void nngp_shape_##NAME(int m, int D, int *blocks_per_sm, int *loc_per_warp);
 NNGP_DECLARE_FAMILY(f64_exp)
 NNGP_DECLARE_FAMILY(f64_m32)
 NNGP_DECLARE_FAMILY(f64_m52)
@@ -47,18 +47,16 @@ void free_dev(P *&p)
     p = nullptr;
 }
 
-int locations_per_warp(int m) { return m <= 15 ? 8 : (m <= 31 ? 4 : 2); }
-
-int family_occupancy(int dtype, int kernel_id, int m, int D)
+void family_shape(int dtype, int kernel_id, int m, int D, int *per_sm, int *lpw)
 {
     if (dtype == NNGP_F64) {
-        if (kernel_id == NNGP_EXPONENTIAL) return nngp_occupancy_f64_exp(m, D);
-        if (kernel_id == NNGP_MATERN32) return nngp_occupancy_f64_m32(m, D);
-        return nngp_occupancy_f64_m52(m, D);
+        if (kernel_id == NNGP_EXPONENTIAL) return nngp_shape_f64_exp(m, D, per_sm, lpw);
+        if (kernel_id == NNGP_MATERN32) return nngp_shape_f64_m32(m, D, per_sm, lpw);
+        return nngp_shape_f64_m52(m, D, per_sm, lpw);
     }
-    if (kernel_id == NNGP_EXPONENTIAL) return nngp_occupancy_f32_exp(m, D);
-    if (kernel_id == NNGP_MATERN32) return nngp_occupancy_f32_m32(m, D);
-    return nngp_occupancy_f32_m52(m, D);
+    if (kernel_id == NNGP_EXPONENTIAL) return nngp_shape_f32_exp(m, D, per_sm, lpw);
+    if (kernel_id == NNGP_MATERN32) return nngp_shape_f32_m32(m, D, per_sm, lpw);
+    return nngp_shape_f32_m52(m, D, per_sm, lpw);
 }
 
 cudaError_t family_launch(int dtype, int kernel_id, int m, int D, const EvalArgs &a, int K, int grid_x,
@@ -77,8 +75,9 @@ cudaError_t family_launch(int dtype, int kernel_id, int m, int D, const EvalArgs
 // grid.x for nloc locations: enough resident blocks to fill every SM, never more than the work
 int grid_for(nngp_handle *h, int kernel_id, int64_t nloc)
 {
-    const int per_sm = family_occupancy(h->dtype, kernel_id, h->m, h->D);
-    const int64_t groups = (nloc + locations_per_warp(h->m) - 1) / locations_per_warp(h->m);
+    int per_sm = 1, lpw = 8;
+    family_shape(h->dtype, kernel_id, h->m, h->D, &per_sm, &lpw);
+    const int64_t groups = (nloc + lpw - 1) / lpw;
     const int64_t need = (groups + 3) / 4;  // 4 warps per block
     int64_t g = int64_t(h->num_sms) * per_sm;
     if (g > need) g = need;

@@ -199,13 +199,40 @@ class NNGP(object):
         params = np.atleast_2d(np.asarray(params, dtype=np.float64))
         if params.shape[1] == 3:
             params = np.concatenate([params, np.zeros((params.shape[0], 1))], axis=1)
+        if self._world > 1:
+            return self._loglik_batch_sharded(params)
         total = np.zeros((params.shape[0], _lib.NSTAT))
         for c in range(self._y2d.shape[1]):
             self._set_column(c)
             total += self._engine.loglik(self._kernel.kernel_id, params)
-        if self._world > 1:
-            total = _dist.allreduce_stats(total, self._group)
         return total
+
+    def _loglik_batch_sharded(self, params):
+        """Multi-GPU evaluation with no host round trip between the kernel and the collective: the
+        fused kernel writes this rank's (K, 3) partial statistics into a torch CUDA tensor on torch's
+        current stream, NCCL sums them over NVLink on the same stream, one D2H copy returns them."""
+        import torch
+
+        dev = torch.device("cuda", self._engine.device)
+        K = params.shape[0]
+        with torch.cuda.device(dev):
+            stream = torch.cuda.current_stream()
+            if stream.cuda_stream == 0:  # the C ABI reads NULL as "the handle's stream": use a real one
+                if getattr(self, "_stream", None) is None:
+                    self._stream = torch.cuda.Stream()
+                stream = self._stream
+            with torch.cuda.stream(stream):
+                d_prm = torch.from_numpy(params).to(dev, non_blocking=True)
+                total = torch.zeros((K, _lib.NSTAT), dtype=torch.float64, device=dev)
+                d_out = torch.empty_like(total)
+                for c in range(self._y2d.shape[1]):
+                    self._set_column(c)
+                    self._engine.loglik_device(self._kernel.kernel_id, d_prm.data_ptr(), K, d_out.data_ptr(),
+                                               stream.cuda_stream)
+                    total += d_out
+                _dist.allreduce_stats(total, self._group)
+                out = total.cpu().numpy()
+        return out
 
     def loglik_terms(self, sigma2=None, phi=None, tau2=None):
         """(sum_i log F_i, sum_i r_i^2 / F_i) -- the reduction BASELINE.json's north_star names."""

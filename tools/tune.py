@@ -32,8 +32,8 @@ for dtype in dtypes:
         table = e.get_neighbors()
     else:
         e.set_neighbors(table)
-    for knob in os.environ.get("KNOBS", "3,2,4").split(","):
-        os.environ["NNGP_TUNE_MINB"] = knob
+    for knob in os.environ.get("KNOBS", "default").split(","):
+        os.environ["NNGP_TUNE_SHAPE"] = knob
         ts = []
         for it in range(13):
             flush.zero_()
@@ -44,4 +44,4 @@ for dtype in dtypes:
             torch.cuda.synchronize()
             if it >= 3:
                 ts.append(a.elapsed_time(b))
-        print(f"{name} {dtype} minb={knob}: {np.mean(ts):.4f} ms (min {np.min(ts):.4f})  stats={out.cpu().numpy()[0].tolist()}", flush=True)
+        print(f"{name} {dtype} shape={knob}: {np.mean(ts):.4f} ms (min {np.min(ts):.4f})  stats={out.cpu().numpy()[0].tolist()}", flush=True)
