@@ -238,7 +238,7 @@ __host__ __device__ constexpr int tile_stride() { return (P * (P - 1) / 2 + 7) /
 
 // Per-warp shared-memory carve-up (bytes).  Everything a warp touches is private to it, so the
 // main loop needs __syncwarp only.
-template <typename T, int G, int R, bool DIM3, bool ROLLED>
+template <typename T, int G, int R, bool DIM3, int BUILD>
 struct WarpSmem {
     static constexpr int P = G * R, W = 32 / G;
     // location strides are padded by 16 bytes so the W groups of a warp start in different banks
@@ -250,30 +250,30 @@ struct WarpSmem {
                                                                              // D < 3 records carry it in .z)
     static constexpr size_t idx = size_t(R) * 32 * sizeof(int);          // next group's neighbour indices
     static constexpr size_t acc = size_t(3) * 32 * sizeof(double);       // per-lane partial sums
-    static constexpr size_t tile = ROLLED ? (size_t(W) * tile_stride<P>() * sizeof(T) + 15) / 16 * 16 : 0;  // covariance entries
+    static constexpr size_t tile = BUILD == 1 ? (size_t(W) * tile_stride<P>() * sizeof(T) + 15) / 16 * 16 : 0;  // pair-indexed tile
     static constexpr size_t stage = size_t(W) * stage_stride;                      // scaled coordinates
     static constexpr size_t dump = size_t(P) * P * sizeof(T);            // emit only: one location's factor
     __host__ __device__ static constexpr size_t total(bool emit) { return rec + e2 + idx + acc + tile + stage + (emit ? dump : 0); }
 };
 
 // block-shared part: exp table + the launch's pair list (one packed word per pair)
-template <int P, bool ROLLED>
-__host__ __device__ constexpr size_t block_smem() { return kExpTab * sizeof(double) + (ROLLED ? (size_t(P) * (P - 1) / 2 + 64) * 8 : 0); }
+template <int P, int BUILD>
+__host__ __device__ constexpr size_t block_smem() { return kExpTab * sizeof(double) + (BUILD == 1 ? (size_t(P) * (P - 1) / 2 + 64) * 8 : 0); }
 
 // dynamic shared memory needed by one block
-template <typename T, int G, int R, bool DIM3, bool ROLLED>
+template <typename T, int G, int R, bool DIM3, int BUILD>
 constexpr size_t smem_bytes(bool emit)
 {
-    return block_smem<G * R, ROLLED>() + size_t(kWarps) * WarpSmem<T, G, R, DIM3, ROLLED>::total(emit);
+    return block_smem<G * R, BUILD>() + size_t(kWarps) * WarpSmem<T, G, R, DIM3, BUILD>::total(emit);
 }
 
-template <typename T, int G, int R, int KERN, bool DIM3, int MINB, bool ROLLED>
+template <typename T, int G, int R, int KERN, bool DIM3, int MINB, int BUILD>
 __global__ void __launch_bounds__(kThreads, MINB) fused_loglik_kernel(const EvalArgs a)
 {
     constexpr int P = G * R;   // rows of the augmented matrix
     constexpr int W = 32 / G;  // locations per warp
     using Pt = StagePt<T, DIM3>;
-    using WS = WarpSmem<T, G, R, DIM3, ROLLED>;
+    using WS = WarpSmem<T, G, R, DIM3, BUILD>;
 
     extern __shared__ __align__(32) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31;
@@ -283,7 +283,7 @@ __global__ void __launch_bounds__(kThreads, MINB) fused_loglik_kernel(const Eval
 
     T *exp_tab = reinterpret_cast<T *>(smem_raw);  // sigma2 * 2^(j/64) (fp64 path only)
     uint2 *pair_lut = reinterpret_cast<uint2 *>(smem_raw + kExpTab * sizeof(double));
-    unsigned char *wbase = smem_raw + block_smem<P, ROLLED>() + size_t(warp) * WS::total(a.emit != 0);
+    unsigned char *wbase = smem_raw + block_smem<P, BUILD>() + size_t(warp) * WS::total(a.emit != 0);
     unsigned char *recbuf = wbase + g * WS::rec_stride;  // this location's records (16-byte aligned)
     double *e2buf = reinterpret_cast<double *>(wbase + WS::rec);
     int *idxbuf = reinterpret_cast<int *>(wbase + WS::rec + WS::e2) + lane;          // [s * 32]
@@ -309,7 +309,7 @@ __global__ void __launch_bounds__(kThreads, MINB) fused_loglik_kernel(const Eval
     const int rows_in_play = m + 1;
     const int npairs = rows_in_play * (rows_in_play - 1) / 2;
     const int nbatch = (npairs + G * CB - 1) / (G * CB);  // build-loop trips; the list is padded to it
-    if (ROLLED) {
+    if (BUILD == 1) {
         for (int t = threadIdx.x; t < nbatch * G * CB; t += kThreads) {
             const int tt = t < npairs ? t : npairs - 1;  // padding repeats the last pair (same value, same slot)
             int ia = int((1.0f + sqrtf(1.0f + 8.0f * float(tt))) * 0.5f);
@@ -426,7 +426,7 @@ __global__ void __launch_bounds__(kThreads, MINB) fused_loglik_kernel(const Eval
 
         // ---- stage 2: covariance build ------------------------------------------------------------
         T A[R][P];
-        if constexpr (ROLLED) {
+        if constexpr (BUILD == 1) {
         // A rolled loop over this lane's share of the pair list, CB pairs in lock step (independent
         // dependency chains: one chain cannot fill the FP64 pipe -- 8-cycle DFMA latency).  Operands
         // come from the staged coordinates, results go to the location's tile: nothing here needs a
@@ -672,23 +672,23 @@ __global__ void __launch_bounds__(kThreads, MINB) fused_loglik_kernel(const Eval
 }
 
 // ---- host-side dispatch of one (T, KERN) family -------------------------------------------------
-template <typename T, int G, int R, int KERN, bool DIM3, int MINB, bool ROLLED>
+template <typename T, int G, int R, int KERN, bool DIM3, int MINB, int BUILD>
 cudaError_t launch_one(const EvalArgs &a, int K, int grid_x, cudaStream_t stream)
 {
-    auto kern = fused_loglik_kernel<T, G, R, KERN, DIM3, MINB, ROLLED>;
-    const size_t smem = smem_bytes<T, G, R, DIM3, ROLLED>(a.emit != 0);
+    auto kern = fused_loglik_kernel<T, G, R, KERN, DIM3, MINB, BUILD>;
+    const size_t smem = smem_bytes<T, G, R, DIM3, BUILD>(a.emit != 0);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     kern<<<dim3(grid_x, K, 1), kThreads, smem, stream>>>(a);
     return cudaGetLastError();
 }
 
-template <typename T, int G, int R, int KERN, bool DIM3, int MINB, bool ROLLED>
+template <typename T, int G, int R, int KERN, bool DIM3, int MINB, int BUILD>
 int blocks_per_sm()
 {
-    auto kern = fused_loglik_kernel<T, G, R, KERN, DIM3, MINB, ROLLED>;
+    auto kern = fused_loglik_kernel<T, G, R, KERN, DIM3, MINB, BUILD>;
     int nb = 0;
-    const size_t smem = smem_bytes<T, G, R, DIM3, ROLLED>(false);
+    const size_t smem = smem_bytes<T, G, R, DIM3, BUILD>(false);
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, kThreads, smem) != cudaSuccess) nb = 1;
     return nb < 1 ? 1 : nb;
@@ -710,31 +710,30 @@ struct Launcher {
     const EvalArgs &a;
     int K, grid_x;
     cudaStream_t stream;
-    template <int G, int R, bool DIM3, int MINB, bool ROLLED>
-    cudaError_t run() const { return launch_one<T, G, R, KERN, DIM3, MINB, ROLLED>(a, K, grid_x, stream); }
+    template <int G, int R, bool DIM3, int MINB, int BUILD>
+    cudaError_t run() const { return launch_one<T, G, R, KERN, DIM3, MINB, BUILD>(a, K, grid_x, stream); }
 };
 template <typename T, int KERN>
 struct Describer {
-    template <int G, int R, bool DIM3, int MINB, bool ROLLED>
-    ShapeInfo run() const { return ShapeInfo{blocks_per_sm<T, G, R, KERN, DIM3, MINB, ROLLED>(), 32 / G}; }
+    template <int G, int R, bool DIM3, int MINB, int BUILD>
+    ShapeInfo run() const { return ShapeInfo{blocks_per_sm<T, G, R, KERN, DIM3, MINB, BUILD>(), 32 / G}; }
 };
 
 template <typename T, bool DIM3, typename F>
 auto dispatch_shape(int m, const F &f)
 {
     constexpr bool F64 = sizeof(T) == 8;
-#ifdef NNGP_TUNE  // development knob for the m <= 15 shape: NNGP_TUNE_SHAPE = 4x4r | 4x4u | 4x4u3 | 2x8u
+#ifdef NNGP_TUNE  // development knob for the m <= 15 shape: NNGP_TUNE_SHAPE = 4x4r | 4x4u | 4x4u3
     if (const char *e = getenv("NNGP_TUNE_SHAPE"); e && m > 7 && m <= 15 && !DIM3) {
-        if (!strcmp(e, "4x4r")) return f.template run<4, 4, DIM3, 2, true>();
-        if (!strcmp(e, "4x4u")) return f.template run<4, 4, DIM3, 2, false>();
-        if (!strcmp(e, "4x4u3")) return f.template run<4, 4, DIM3, 3, false>();
-        if (!strcmp(e, "2x8u")) return f.template run<2, 8, DIM3, 2, false>();
+        if (!strcmp(e, "4x4r")) return f.template run<4, 4, DIM3, 2, 1>();
+        if (!strcmp(e, "4x4u")) return f.template run<4, 4, DIM3, 2, 0>();
+        if (!strcmp(e, "4x4u3")) return f.template run<4, 4, DIM3, 3, 0>();
     }
 #endif
-    if (m <= 7) return f.template run<4, 2, DIM3, 4, false>();
-    if (m <= 15) return f.template run<4, 4, DIM3, (F64 ? 3 : 4), false>();
-    if (m <= 31) return f.template run<8, 4, DIM3, (F64 ? 2 : 4), true>();
-    return f.template run<16, 3, DIM3, (F64 ? 2 : 4), true>();
+    if (m <= 7) return f.template run<4, 2, DIM3, 4, 0>();
+    if (m <= 15) return f.template run<4, 4, DIM3, (F64 ? 3 : 4), 0>();
+    if (m <= 31) return f.template run<8, 4, DIM3, (F64 ? 2 : 4), 1>();
+    return f.template run<16, 3, DIM3, (F64 ? 2 : 4), 1>();
 }
 
 template <typename T, int KERN>
