@@ -679,6 +679,9 @@ cudaError_t launch_one(const EvalArgs &a, int K, int grid_x, cudaStream_t stream
     const size_t smem = smem_bytes<T, G, R, DIM3, BUILD>(a.emit != 0);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
+#ifdef NNGP_TUNE
+    if (const char *c = getenv("NNGP_TUNE_CARVEOUT")) cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(c));
+#endif
     kern<<<dim3(grid_x, K, 1), kThreads, smem, stream>>>(a);
     return cudaGetLastError();
 }
