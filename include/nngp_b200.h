@@ -80,6 +80,10 @@ int nngp_build_neighbors(nngp_handle *h, int m, int tile_offset, int tile_stride
 /* Injects a table (n x m int32 row-major, -1 padded; valid entries first in each row). */
 int nngp_set_neighbors(nngp_handle *h, const int32_t *idx, int m);
 int nngp_get_neighbors(nngp_handle *h, int32_t *out);
+/* Plain k-NN over all rows, the query itself included (no ordering constraint), same (d2, j) order;
+ * out: n x k int32 on the host.  Replaces the neighbour search inside _init_ws, nngp.py:45-47
+ * (KNeighborsRegressor(5).fit(t, y).predict(s): the mean of y over these rows is `ws`). */
+int nngp_knn_plain(nngp_handle *h, int k, int32_t *out);
 /* Device address of the n x m int32 table (for an NCCL exchange by the caller), or NULL. */
 void *nngp_neighbors_device_ptr(nngp_handle *h);
 

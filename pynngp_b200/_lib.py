@@ -35,6 +35,7 @@ SIGNATURES = {
     "nngp_build_neighbors": (ctypes.c_int, [_handle_p, ctypes.c_int, ctypes.c_int, ctypes.c_int]),
     "nngp_set_neighbors": (ctypes.c_int, [_handle_p, _c_int32_p, ctypes.c_int]),
     "nngp_get_neighbors": (ctypes.c_int, [_handle_p, _c_int32_p]),
+    "nngp_knn_plain": (ctypes.c_int, [_handle_p, ctypes.c_int, _c_int32_p]),
     "nngp_neighbors_device_ptr": (ctypes.c_void_p, [_handle_p]),
     "nngp_loglik": (ctypes.c_int, [_handle_p, ctypes.c_int, _c_double_p, ctypes.c_int, _c_double_p]),
     "nngp_loglik_device": (ctypes.c_int, [_handle_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]),
@@ -146,6 +147,12 @@ class Engine:
     def get_neighbors(self):
         out = np.empty((self.n, self.m), dtype=np.int32)
         self._check(self._lib.nngp_get_neighbors(self._h, out.ctypes.data_as(_c_int32_p)), "nngp_get_neighbors")
+        return out
+
+    def knn_plain(self, k):
+        """(n, k) int32: the k nearest rows of every row, itself included, ascending (d2, j)."""
+        out = np.empty((self.n, int(k)), dtype=np.int32)
+        self._check(self._lib.nngp_knn_plain(self._h, int(k), out.ctypes.data_as(_c_int32_p)), "nngp_knn_plain")
         return out
 
     def neighbors_device_ptr(self):

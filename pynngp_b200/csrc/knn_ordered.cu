@@ -106,7 +106,9 @@ __device__ __forceinline__ double dist2_sk(double qx, double qy, double qz, cons
     return d;
 }
 
-template <bool DIM3>
+// ORDERED: candidates are the predecessors j < i (the NNGP neighbour sets).  !ORDERED: every row j,
+// the query itself included -- the plain k-NN behind the reference's `ws` warm start (nngp.py:45-47).
+template <bool DIM3, bool ORDERED>
 __global__ void __launch_bounds__(TQ) knn_ordered_kernel(const double4 *__restrict__ pts, int64_t n,
                                                          int m, int ntiles, int tile_offset,
                                                          int tile_stride, unsigned int *tile_counter,
@@ -137,7 +139,7 @@ __global__ void __launch_bounds__(TQ) knn_ordered_kernel(const double4 *__restri
         const int64_t i = q0 + tid;
         const bool live = i < n;
         const int64_t last_q = (q0 + TQ < n ? q0 + TQ : n) - 1;  // largest live query of the tile
-        const int64_t ncand = last_q;                            // candidates 0 .. last_q-1
+        const int64_t ncand = ORDERED ? last_q : n;              // candidates 0 .. last_q-1 (or all rows)
         const int nct = int((ncand + TC - 1) / TC);
 
         double qx = 0.0, qy = 0.0, qz = 0.0;
@@ -173,7 +175,7 @@ __global__ void __launch_bounds__(TQ) knn_ordered_kernel(const double4 *__restri
             phase ^= 1u << s;
             const double2 *rec = reinterpret_cast<const double2 *>(cand + size_t(s) * TC);
 
-            if (c0 + jn <= q0 && (jn & 3) == 0) {
+            if ((!ORDERED || c0 + jn <= q0) && (jn & 3) == 0) {
                 // every candidate precedes every query of the tile: no j < i test
                 for (int jj = 0; jj < jn; jj += 4) {
                     const double d0 = dist2_sk<DIM3>(qx, qy, qz, rec + 2 * (jj + 0));
@@ -193,7 +195,7 @@ __global__ void __launch_bounds__(TQ) knn_ordered_kernel(const double4 *__restri
                 // diagonal / ragged tile: only predecessors j < i count
                 int lim = 0;
                 if (live) {
-                    const int64_t v = i - c0;
+                    const int64_t v = ORDERED ? i - c0 : int64_t(jn);
                     lim = v < 0 ? 0 : (v > jn ? jn : int(v));
                 }
                 for (int jj = 0; jj < jn; ++jj) {
@@ -227,21 +229,22 @@ inline size_t smem_bytes(int m)
 
 }  // namespace nngp_knn
 
-cudaError_t launch_knn_ordered(nngp_handle *h, int m, int tile_offset, int tile_stride,
-                               cudaStream_t stream)
+static cudaError_t launch_knn(nngp_handle *h, bool ordered, int m, int tile_offset, int tile_stride,
+                              int32_t *table, cudaStream_t stream)
 {
     using namespace nngp_knn;
     const int64_t n = h->n;
     const int ntiles = int((n + TQ - 1) / TQ);
     cudaError_t e;
     if (tile_stride > 1) {
-        fill_i32_kernel<<<h->num_sms * 4, 256, 0, stream>>>(h->nbr, n * int64_t(m), NNGP_ROW_UNSET);
+        fill_i32_kernel<<<h->num_sms * 4, 256, 0, stream>>>(table, n * int64_t(m), NNGP_ROW_UNSET);
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
         ++h->launches;
     }
     if ((e = cudaMemsetAsync(h->d_tile_counter, 0, sizeof(unsigned int), stream)) != cudaSuccess) return e;
     const size_t smem = smem_bytes(m);
-    auto kern = h->D == 3 ? knn_ordered_kernel<true> : knn_ordered_kernel<false>;
+    auto kern = ordered ? (h->D == 3 ? knn_ordered_kernel<true, true> : knn_ordered_kernel<false, true>)
+                        : (h->D == 3 ? knn_ordered_kernel<true, false> : knn_ordered_kernel<false, false>);
     if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess)
         return e;
     int per_sm = 1;
@@ -250,8 +253,17 @@ cudaError_t launch_knn_ordered(nngp_handle *h, int m, int tile_offset, int tile_
     const int my_tiles = (ntiles - tile_offset + tile_stride - 1) / tile_stride;
     int grid = h->num_sms * per_sm;
     if (grid > my_tiles) grid = my_tiles > 0 ? my_tiles : 1;
-    kern<<<grid, TQ, smem, stream>>>(h->pts, n, m, ntiles, tile_offset, tile_stride, h->d_tile_counter,
-                                     h->nbr);
+    kern<<<grid, TQ, smem, stream>>>(h->pts, n, m, ntiles, tile_offset, tile_stride, h->d_tile_counter, table);
     ++h->launches;
     return cudaGetLastError();
+}
+
+cudaError_t launch_knn_ordered(nngp_handle *h, int m, int tile_offset, int tile_stride, cudaStream_t stream)
+{
+    return launch_knn(h, true, m, tile_offset, tile_stride, h->nbr, stream);
+}
+
+cudaError_t launch_knn_plain(nngp_handle *h, int k, int32_t *d_table, cudaStream_t stream)
+{
+    return launch_knn(h, false, k, 0, 1, d_table, stream);
 }

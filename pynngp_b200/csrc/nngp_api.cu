@@ -273,6 +273,22 @@ int nngp_get_neighbors(nngp_handle *h, int32_t *out)
     return NNGP_OK;
 }
 
+int nngp_knn_plain(nngp_handle *h, int k, int32_t *out)
+{
+    if (!h) return fail(nullptr, NNGP_EINVAL, "null handle");
+    if (!h->pts) return fail(h, NNGP_ESTATE, "nngp_set_data has not been called");
+    if (!out || k < 1 || k > NNGP_MAX_M) return fail(h, NNGP_EINVAL, "need out != NULL and 1 <= k <= 32");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    int32_t *d_tab = nullptr;
+    CUDA_TRY(h, cudaMalloc(&d_tab, sizeof(int32_t) * (size_t)h->n * k));
+    cudaError_t e = launch_knn_plain(h, k, d_tab, h->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out, d_tab, sizeof(int32_t) * (size_t)h->n * k, cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    cudaFree(d_tab);
+    if (e != cudaSuccess) return cuda_fail(h, e, "nngp_knn_plain");
+    return NNGP_OK;
+}
+
 void *nngp_neighbors_device_ptr(nngp_handle *h) { return (h && h->has_nbr) ? (void *)h->nbr : nullptr; }
 
 int nngp_loglik_device(nngp_handle *h, int kernel_id, const double *d_params, int K, double *d_out, void *stream)

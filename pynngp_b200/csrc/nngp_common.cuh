@@ -67,5 +67,5 @@ cudaError_t launch_fused_loglik(nngp_handle *h, int kernel_id, const EvalArgs &a
                                 cudaStream_t stream);
 cudaError_t launch_knn_ordered(nngp_handle *h, int m, int tile_offset, int tile_stride,
                                cudaStream_t stream);
+cudaError_t launch_knn_plain(nngp_handle *h, int k, int32_t *d_table, cudaStream_t stream);
 cudaError_t launch_fma_peak(nngp_handle *h, int dtype, int iters, double *instr_per_s);
-int fused_grid_blocks(nngp_handle *h, int kernel_id, int64_t nloc);

@@ -150,9 +150,15 @@ class NNGP(object):
 
     @property
     def ws(self):
-        # nngp.py:45-47: 5-NN uniform-mean warm start of the latent field (Gibbs state, not used by
-        # the likelihood).  Not on the hot path; not built yet.
-        raise NotImplementedError("ws (Gibbs warm start, nngp.py:45-47) is outside the likelihood hot path")
+        """Warm start of the latent field at the reference sites (nngp.py:45-47): the uniform mean of y
+        over the 5 nearest sites of each site, itself included -- what scikit-learn's
+        ``KNeighborsRegressor(5, 'uniform').fit(t, y).predict(s)`` returns for S = T.  Computed lazily
+        on the GPU (plain k-NN kernel) the first time it is read; not used by the likelihood."""
+        if self._ws is None:
+            k = min(5, len(self._coords))
+            idx = self._engine.knn_plain(k)
+            self._ws = self._y2d[idx].mean(axis=1).reshape(np.shape(self.y))
+        return self._ws
 
     # ---- parameters -------------------------------------------------------------------------------
     def _params(self, sigma2=None, phi=None, tau2=None):

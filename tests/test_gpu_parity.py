@@ -322,3 +322,27 @@ def test_two_gpu_sharded_equals_single():
                        capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
     assert "multi-gpu ok" in r.stdout
+
+
+def test_ws_warm_start_matches_sklearn():
+    """`ws` (nngp.py:45-47) = KNeighborsRegressor(5, 'uniform').fit(t, y).predict(s) with S = T; the
+    plain k-NN table itself is checked against an exact numpy scan with the (d2, j) order."""
+    import pyNNGP
+    from sklearn.neighbors import KNeighborsRegressor
+
+    for D, n in ((2, 3000), (3, 1500), (1, 700)):
+        s, y = synthetic(n, D, 60 + D)
+        obj = pyNNGP.NNGP(s, y, 0.0, "S=T", 4, None)
+        want = KNeighborsRegressor(n_neighbors=5, weights="uniform").fit(s, y).predict(s)
+        np.testing.assert_allclose(obj.ws, want, rtol=1e-13, atol=1e-15)
+        idx = obj._engine.knn_plain(5)
+        for i in (0, 1, n // 2, n - 1):
+            d2 = orc.np_dist2(s[i], s)
+            assert np.array_equal(idx[i], np.lexsort((np.arange(n), d2))[:5])
+            assert idx[i, 0] == i  # the site itself comes first (distance 0)
+    # 2-column response as in the reference's own test (tests/test_init.py:11)
+    s, y = synthetic(500, 2, 9)
+    y2 = np.stack([y, -2 * y], axis=1)
+    obj = pyNNGP.NNGP(s, y2, 0.0, "S=T", 3, None)
+    want = KNeighborsRegressor(n_neighbors=5).fit(s, y2).predict(s)
+    np.testing.assert_allclose(obj.ws, want, rtol=1e-13, atol=1e-15)
