@@ -288,8 +288,8 @@ def run_ours(args, cfg):
     hbm_ach = nloc * hbm_bytes_per_location(cfg["m"], cfg["D"]) / (kern_ms * 1e-3) / 1e9
     traffic = None
     tr_path = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tr_path):
-        traffic = json.load(open(tr_path)).get("fused_dram_bytes_per_launch")
+    if os.path.exists(tr_path) and args.config == "cfg3" and world == 1 and args.dtype == "float64":
+        traffic = json.load(open(tr_path)).get("fused_dram_bytes_per_launch")  # ncu capture of this very workload
     roofline = {
         "bound": "fp64" if args.dtype == "float64" else "fp32",
         "achieved": achieved_tflops, "peak": peak_tflops, "unit": "TFLOP/s", "frac": achieved_tflops / peak_tflops,

@@ -233,6 +233,31 @@ __device__ __forceinline__ T grp_bcast(T v, int src)
 // Shared-memory tile of one location: the strict lower triangle of the augmented matrix, row-major
 // (entry (a, b), a > b, at a(a-1)/2 + b).  The per-location stride is padded so the W locations of a
 // warp start 16 bytes (mod 128) apart: no systematic bank aliasing between the lane groups.
+// Column-major enumeration of the (row block s, column j) pairs a lane owns in the row-owner layout:
+// column j is needed by the row blocks s >= (j + 1) / G.  Evaluated at compile time (unrolled callers).
+template <int G, int R>
+__host__ __device__ constexpr int pair_col(int t)
+{
+    int j = 0;
+    for (; j < G * R - 1; ++j) {
+        const int cnt = R - (j + 1) / G;
+        if (t < cnt) break;
+        t -= cnt;
+    }
+    return j;
+}
+template <int G, int R>
+__host__ __device__ constexpr int pair_slot(int t)
+{
+    int j = 0;
+    for (; j < G * R - 1; ++j) {
+        const int cnt = R - (j + 1) / G;
+        if (t < cnt) break;
+        t -= cnt;
+    }
+    return (j + 1) / G + t;
+}
+
 template <int P>
 __host__ __device__ constexpr int tile_stride() { return (P * (P - 1) / 2 + 7) / 8 * 8 + 4; }
 
@@ -477,35 +502,33 @@ __global__ void __launch_bounds__(kThreads, MINB) fused_loglik_kernel(const Eval
                 A[s][s * G + G - 1] = dg[s];  // last column of the diagonal block: lane G-1's diagonal
             }
         } else {
-            // Row-owner build, fully unrolled: for column j the lane evaluates the pairs (row, j) of up
-            // to CB of its rows in lock step (independent chains sharing one column point) and the
-            // results go straight to the row registers.  Used where the rows-per-lane count makes this
-            // layout nearly balanced (G = 2) and the shuffle / shared-memory pipe is the scarcer unit.
+            // Row-owner build, fully unrolled.  The lane's pairs (row block s, column j) are enumerated
+            // column-major at compile time and evaluated CB at a time in lock step -- always CB
+            // independent chains, whichever rows/columns they belong to (batching by column alone runs
+            // out of parallelism on the late columns, which only the last row block needs) -- and the
+            // results go straight to the row registers.
             constexpr int CB = 4;
+            constexpr int NP = G * R * (R + 1) / 2 - R;  // sum over s of (s*G + G - 1)
 #pragma unroll
-            for (int j = 0; j < P - 1; ++j) {
-                const Pt cj = stage[j];
+            for (int t0 = 0; t0 < NP; t0 += CB) {
+                T d2[CB];
 #pragma unroll
-                for (int s0 = 0; s0 < R; s0 += CB) {
-                    if ((((s0 + CB < R) ? s0 + CB : R) - 1) * G + G - 1 > j) {
-                        T d2[CB];
+                for (int b = 0; b < CB; ++b) {
+                    const int t = (t0 + b < NP) ? t0 + b : NP - 1;
+                    const int s = pair_slot<G, R>(t), j = pair_col<G, R>(t);
+                    const Pt cj = stage[j];
+                    const T dx = rx[s] - cj.x, dy = ry[s] - cj.y;
+                    d2[b] = t_fma(dy, dy, t_fma(dx, dx, tiny_seed<T>()));
+                    if constexpr (DIM3) { const T dz = rz[s] - cj.z; d2[b] = t_fma(dz, dz, d2[b]); }
+                }
+                cov_batch<KERN, CB>(d2, exp_tab, sigma2);
 #pragma unroll
-                        for (int b = 0; b < CB; ++b) {
-                            const int s = (s0 + b < R) ? s0 + b : R - 1;
-                            const T dx = rx[s] - cj.x, dy = ry[s] - cj.y;
-                            d2[b] = t_fma(dy, dy, t_fma(dx, dx, tiny_seed<T>()));
-                            if constexpr (DIM3) { const T dz = rz[s] - cj.z; d2[b] = t_fma(dz, dz, d2[b]); }
-                        }
-                        cov_batch<KERN, CB>(d2, exp_tab, sigma2);
-#pragma unroll
-                        for (int b = 0; b < CB; ++b) {
-                            const int s = s0 + b;
-                            if (s < R && s * G + G - 1 > j) {
-                                T v = d2[b];
-                                if (j >= s * G) v = (s * G + q == j) ? dg[s] : v;  // diagonal block only
-                                A[s][j] = v;
-                            }
-                        }
+                for (int b = 0; b < CB; ++b) {
+                    if (t0 + b < NP) {
+                        const int s = pair_slot<G, R>(t0 + b), j = pair_col<G, R>(t0 + b);
+                        T v = d2[b];
+                        if (j >= s * G) v = (s * G + q == j) ? dg[s] : v;  // diagonal block only
+                        A[s][j] = v;
                     }
                 }
             }
