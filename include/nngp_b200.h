@@ -77,6 +77,19 @@ int nngp_set_shard(nngp_handle *h, int64_t lo, int64_t hi);
 #define NNGP_KNN_TILE 128
 #define NNGP_ROW_UNSET (-2)
 int nngp_build_neighbors(nngp_handle *h, int m, int tile_offset, int tile_stride);
+/* Stage 1 in sub-quadratic time (same contract and bit-identical output: _make_s_neighbor_sets,
+ * nngp.py:49-62): rows [row_lo, row_hi) of the table are searched over a uniform cell grid, level by
+ * level of the ordering (knn_grid.cu); rows outside the range hold NNGP_ROW_UNSET or their correct
+ * value, so ranks that each build their own shard assemble the table with an elementwise MAX.
+ * algo: NNGP_KNN_AUTO = grid unless the coordinates are non-finite or so clustered that the cell
+ * histogram predicts more work than brute force; NNGP_KNN_GRID / NNGP_KNN_BRUTE force one. */
+enum { NNGP_KNN_AUTO = 0, NNGP_KNN_GRID = 1, NNGP_KNN_BRUTE = 2 };
+int nngp_build_neighbors_grid(nngp_handle *h, int m, int64_t row_lo, int64_t row_hi, int algo);
+/* Grid search knobs: cells hold lambda_scale * (m + 2 sqrt m) / unit-ball-volume usable points
+ * (default 1.0); rows below brute_rows (default 8192) always use brute force. */
+int nngp_set_knn_tuning(nngp_handle *h, double lambda_scale, int64_t brute_rows);
+/* 1 if the last nngp_build_neighbors_grid call went through the grid, 0 if it fell back. */
+int nngp_knn_used_grid(const nngp_handle *h);
 /* Injects a table (n x m int32 row-major, -1 padded; valid entries first in each row). */
 int nngp_set_neighbors(nngp_handle *h, const int32_t *idx, int m);
 int nngp_get_neighbors(nngp_handle *h, int32_t *out);

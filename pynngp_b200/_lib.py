@@ -33,6 +33,9 @@ SIGNATURES = {
     "nngp_set_y": (ctypes.c_int, [_handle_p, _c_double_p]),
     "nngp_set_shard": (ctypes.c_int, [_handle_p, ctypes.c_int64, ctypes.c_int64]),
     "nngp_build_neighbors": (ctypes.c_int, [_handle_p, ctypes.c_int, ctypes.c_int, ctypes.c_int]),
+    "nngp_build_neighbors_grid": (ctypes.c_int, [_handle_p, ctypes.c_int, ctypes.c_int64, ctypes.c_int64, ctypes.c_int]),
+    "nngp_set_knn_tuning": (ctypes.c_int, [_handle_p, ctypes.c_double, ctypes.c_int64]),
+    "nngp_knn_used_grid": (ctypes.c_int, [_handle_p]),
     "nngp_set_neighbors": (ctypes.c_int, [_handle_p, _c_int32_p, ctypes.c_int]),
     "nngp_get_neighbors": (ctypes.c_int, [_handle_p, _c_int32_p]),
     "nngp_knn_plain": (ctypes.c_int, [_handle_p, ctypes.c_int, _c_int32_p]),
@@ -135,6 +138,21 @@ class Engine:
         self._check(self._lib.nngp_build_neighbors(self._h, int(m), int(tile_offset), int(tile_stride)),
                     "nngp_build_neighbors")
         self.m = int(m)
+
+    def build_neighbors_grid(self, m, row_lo=0, row_hi=None, algo="auto"):
+        """Stage 1 through the cell-grid search (bit-identical to build_neighbors); rows outside
+        [row_lo, row_hi) hold ROW_UNSET or their correct value."""
+        row_hi = self.n if row_hi is None else row_hi
+        code = {"auto": 0, "grid": 1, "brute": 2}[algo]
+        self._check(self._lib.nngp_build_neighbors_grid(self._h, int(m), int(row_lo), int(row_hi), code),
+                    "nngp_build_neighbors_grid")
+        self.m = int(m)
+
+    def set_knn_tuning(self, lambda_scale=1.0, brute_rows=8192):
+        self._check(self._lib.nngp_set_knn_tuning(self._h, float(lambda_scale), int(brute_rows)), "nngp_set_knn_tuning")
+
+    def knn_used_grid(self):
+        return bool(self._lib.nngp_knn_used_grid(self._h))
 
     def set_neighbors(self, table):
         table = np.ascontiguousarray(table, dtype=np.int32)

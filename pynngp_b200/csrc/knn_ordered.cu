@@ -230,10 +230,10 @@ inline size_t smem_bytes(int m)
 }  // namespace nngp_knn
 
 static cudaError_t launch_knn(nngp_handle *h, bool ordered, int m, int tile_offset, int tile_stride,
-                              int32_t *table, cudaStream_t stream)
+                              int32_t *table, cudaStream_t stream, int64_t n_rows = -1)
 {
     using namespace nngp_knn;
-    const int64_t n = h->n;
+    const int64_t n = n_rows >= 0 ? n_rows : h->n;  // rows >= n are neither queries nor candidates
     const int ntiles = int((n + TQ - 1) / TQ);
     cudaError_t e;
     if (tile_stride > 1) {
@@ -261,6 +261,11 @@ static cudaError_t launch_knn(nngp_handle *h, bool ordered, int m, int tile_offs
 cudaError_t launch_knn_ordered(nngp_handle *h, int m, int tile_offset, int tile_stride, cudaStream_t stream)
 {
     return launch_knn(h, true, m, tile_offset, tile_stride, h->nbr, stream);
+}
+
+cudaError_t launch_knn_brute_rows(nngp_handle *h, int m, int64_t n_rows, int32_t *d_table, cudaStream_t stream)
+{
+    return launch_knn(h, true, m, 0, 1, d_table, stream, n_rows);
 }
 
 cudaError_t launch_knn_plain(nngp_handle *h, int k, int32_t *d_table, cudaStream_t stream)

@@ -1,8 +1,10 @@
 // nngp_api.cu -- the C ABI of libnngp_b200.so (include/nngp_b200.h): handle, uploads, dispatch.
 // No CPU fallback exists anywhere in this library: every compute entry point launches a kernel.
+#include <math.h>
 #include <stdio.h>
 #include <string.h>
 
+#include <cmath>
 #include <vector>
 
 #include "nngp_common.cuh"
@@ -187,11 +189,20 @@ int nngp_set_data(nngp_handle *h, const double *coords, int64_t n, int D, const 
     h->n = n; h->D = D; h->lo = 0; h->hi = n;
     // pack {x, y, z, yval} records on the host, one upload
     std::vector<double4> rec((size_t)n);
+    double bl[3] = {INFINITY, INFINITY, INFINITY}, bh[3] = {-INFINITY, -INFINITY, -INFINITY};
+    bool finite = true;
     for (int64_t i = 0; i < n; ++i) {
         const double *c = coords + i * D;
+        for (int d = 0; d < D; ++d) {  // bounding box for the grid search of stage 1
+            finite &= std::isfinite(c[d]);
+            bl[d] = c[d] < bl[d] ? c[d] : bl[d];
+            bh[d] = c[d] > bh[d] ? c[d] : bh[d];
+        }
         // D < 3: the unused z slot carries eps2 so the fused kernel gathers one record per neighbour
         rec[(size_t)i] = make_double4(c[0], D > 1 ? c[1] : 0.0, D > 2 ? c[2] : (eps2 ? eps2[i] : 0.0), y[i]);
     }
+    for (int d = 0; d < 3; ++d) { h->bb_lo[d] = d < D ? bl[d] : 0.0; h->bb_hi[d] = d < D ? bh[d] : 0.0; }
+    h->bb_finite = finite;
     CUDA_TRY(h, cudaMalloc(&h->pts, sizeof(double4) * (size_t)n));
     CUDA_TRY(h, cudaMemcpyAsync(h->pts, rec.data(), sizeof(double4) * (size_t)n, cudaMemcpyHostToDevice, h->stream));
     if (eps2 && D > 2) {
@@ -248,6 +259,44 @@ int nngp_build_neighbors(nngp_handle *h, int m, int tile_offset, int tile_stride
     return NNGP_OK;
 }
 
+int nngp_build_neighbors_grid(nngp_handle *h, int m, int64_t row_lo, int64_t row_hi, int algo)
+{
+    if (!h) return fail(nullptr, NNGP_EINVAL, "null handle");
+    if (!h->pts) return fail(h, NNGP_ESTATE, "nngp_set_data has not been called");
+    if (row_lo < 0 || row_hi < row_lo || row_hi > h->n) return fail(h, NNGP_EINVAL, "need 0 <= row_lo <= row_hi <= n");
+    if (algo != NNGP_KNN_AUTO && algo != NNGP_KNN_GRID && algo != NNGP_KNN_BRUTE)
+        return fail(h, NNGP_EINVAL, "algo must be NNGP_KNN_AUTO, NNGP_KNN_GRID or NNGP_KNN_BRUTE");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    int rc = alloc_nbr(h, m);
+    if (rc) return rc;
+    int used = 0;
+    if (algo != NNGP_KNN_BRUTE) {
+        CUDA_TRY(h, launch_knn_grid(h, true, m, row_lo, row_hi, h->nbr, h->stream, algo == NNGP_KNN_GRID, &used));
+        if (!used && algo == NNGP_KNN_GRID) return fail(h, NNGP_EINVAL, "grid search needs finite coordinates");
+    }
+    if (!used) {
+        // brute force over every row up to row_hi (rows below row_lo come out correct rather than unset)
+        CUDA_TRY(h, launch_knn_brute_rows(h, m, row_hi, h->nbr, h->stream));
+        if (row_hi < h->n)
+            CUDA_TRY(h, launch_fill_i32(h, h->nbr + row_hi * m, (h->n - row_hi) * m, NNGP_ROW_UNSET, h->stream));
+    }
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    h->knn_used_grid = used;
+    h->has_nbr = true;
+    return NNGP_OK;
+}
+
+int nngp_set_knn_tuning(nngp_handle *h, double lambda_scale, int64_t brute_rows)
+{
+    if (!h) return fail(nullptr, NNGP_EINVAL, "null handle");
+    if (!(lambda_scale > 0.0) || brute_rows < 1) return fail(h, NNGP_EINVAL, "need lambda_scale > 0 and brute_rows >= 1");
+    h->knn_lambda_scale = lambda_scale;
+    h->knn_brute_rows = brute_rows;
+    return NNGP_OK;
+}
+
+int nngp_knn_used_grid(const nngp_handle *h) { return h ? h->knn_used_grid : 0; }
+
 int nngp_set_neighbors(nngp_handle *h, const int32_t *idx, int m)
 {
     if (!h) return fail(nullptr, NNGP_EINVAL, "null handle");
@@ -281,7 +330,9 @@ int nngp_knn_plain(nngp_handle *h, int k, int32_t *out)
     CUDA_TRY(h, cudaSetDevice(h->device));
     int32_t *d_tab = nullptr;
     CUDA_TRY(h, cudaMalloc(&d_tab, sizeof(int32_t) * (size_t)h->n * k));
-    cudaError_t e = launch_knn_plain(h, k, d_tab, h->stream);
+    int used = 0;
+    cudaError_t e = launch_knn_grid(h, false, k, 0, h->n, d_tab, h->stream, 0, &used);
+    if (e == cudaSuccess && !used) e = launch_knn_plain(h, k, d_tab, h->stream);
     if (e == cudaSuccess) e = cudaMemcpyAsync(out, d_tab, sizeof(int32_t) * (size_t)h->n * k, cudaMemcpyDeviceToHost, h->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
     cudaFree(d_tab);

@@ -26,6 +26,11 @@ struct nngp_handle {
     int D = 0;
     int m = 0;
     int64_t lo = 0, hi = 0;
+    double bb_lo[3] = {0, 0, 0}, bb_hi[3] = {0, 0, 0};  // bounding box of the coordinates (set_data)
+    bool bb_finite = false;                              // every coordinate finite
+    double knn_lambda_scale = 1.0;                       // grid k-NN: cell occupancy multiplier
+    int knn_used_grid = 0;                               // last stage-1 build went through the grid
+    int64_t knn_brute_rows = 8192;                       // grid k-NN: rows below this use brute force
 
     double4 *pts = nullptr;
     double *eps2 = nullptr;
@@ -68,4 +73,10 @@ cudaError_t launch_fused_loglik(nngp_handle *h, int kernel_id, const EvalArgs &a
 cudaError_t launch_knn_ordered(nngp_handle *h, int m, int tile_offset, int tile_stride,
                                cudaStream_t stream);
 cudaError_t launch_knn_plain(nngp_handle *h, int k, int32_t *d_table, cudaStream_t stream);
+cudaError_t launch_fill_i32(nngp_handle *h, int32_t *p, int64_t count, int32_t v, cudaStream_t stream);
+// brute force restricted to rows [0, n_rows) of the ordering
+cudaError_t launch_knn_brute_rows(nngp_handle *h, int m, int64_t n_rows, int32_t *d_table, cudaStream_t stream);
+// grid search (knn_grid.cu) for rows [row_lo, row_hi); *used = 0 when the data does not suit a grid
+cudaError_t launch_knn_grid(nngp_handle *h, bool ordered, int m, int64_t row_lo, int64_t row_hi, int32_t *table,
+                            cudaStream_t stream, int force, int *used);
 cudaError_t launch_fma_peak(nngp_handle *h, int dtype, int iters, double *instr_per_s);

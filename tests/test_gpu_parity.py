@@ -88,6 +88,110 @@ def test_knn_tile_split_assembles():
     assert (owned == 1).all()
 
 
+# ---- stage 1 through the cell grid: bit-identical to the brute-force kernel --------------------------
+def grid_table(s, m, lam=1.0, brute_rows=128, lo=0, hi=None, algo="grid"):
+    e = engine(s, np.zeros(len(s)))
+    e.set_knn_tuning(lam, brute_rows)
+    e.build_neighbors_grid(m, lo, hi, algo)
+    return e, e.get_neighbors()
+
+
+@pytest.mark.parametrize("name", ["test_init_shape", "cfg1", "d2_m15", "d3_m30", "d1_m5", "d3_m32"])
+def test_knn_grid_matches_reference_golden(golden_dir, name):
+    g = np.load(os.path.join(golden_dir, f"ns_{name}.npz"))
+    for lam in (0.3, 1.0, 3.0):
+        e, got = grid_table(g["coords"], int(g["m"]), lam)
+        assert e.knn_used_grid()
+        assert np.array_equal(got, g["Ns"])
+
+
+def test_knn_grid_ties_duplicates_degenerate(golden_dir):
+    g = np.load(os.path.join(golden_dir, "ns_lattice.npz"))
+    s, m = g["coords"], int(g["m"])
+    for lam in (0.2, 1.0):
+        assert np.array_equal(grid_table(s, m, lam, 128)[1], orc.c_knn_ordered(s, m))
+    rng = np.random.default_rng(5)
+    dup = np.repeat(rng.random((40, 2)), 10, axis=0)[rng.permutation(400)]   # every site 10 times
+    assert np.array_equal(grid_table(dup, 12)[1], orc.c_knn_ordered(dup, 12))
+    same = np.full((300, 3), 0.25)                                           # zero-extent box
+    assert np.array_equal(grid_table(same, 5)[1], orc.c_knn_ordered(same, 5))
+    line = np.stack([rng.random(600), np.full(600, 2.0)], axis=1)            # one collapsed dimension
+    assert np.array_equal(grid_table(line, 9)[1], orc.c_knn_ordered(line, 9))
+    thin = np.stack([rng.random(900), 1e-7 * rng.random(900), rng.random(900)], axis=1)  # extent below a cell
+    assert np.array_equal(grid_table(thin, 16)[1], orc.c_knn_ordered(thin, 16))
+    far = rng.random((700, 2)) * 1e-3 + 1e6                                  # large offset: slack dominates
+    assert np.array_equal(grid_table(far, 10)[1], orc.c_knn_ordered(far, 10))
+
+
+@pytest.mark.parametrize("n,D,m", [(20000, 2, 15), (9000, 3, 30), (5000, 1, 7), (1537, 2, 32), (3000, 3, 1)])
+def test_knn_grid_matches_oracle_mid_size(n, D, m):
+    s, _ = synthetic(n, D, 100 + D)
+    want = orc.c_knn_ordered(s, m, threads=os.cpu_count() or 1)
+    for lam, brute_rows in ((1.0, 128), (0.25, 512), (4.0, 128)):
+        assert np.array_equal(grid_table(s, m, lam, brute_rows)[1], want)
+
+
+def test_knn_grid_clustered_and_auto():
+    rng = np.random.default_rng(11)
+    blobs = np.concatenate([0.5 + 0.01 * rng.standard_normal((15000, 2)), rng.random((5000, 2)),
+                            0.2 + 0.0005 * rng.standard_normal((5000, 2))])
+    s = blobs[rng.permutation(len(blobs))]
+    want = orc.c_knn_ordered(s, 15, threads=os.cpu_count() or 1)
+    e, got = grid_table(s, 15, 1.0, 8192, algo="auto")
+    assert np.array_equal(got, want)
+    assert np.array_equal(grid_table(s, 15, 1.0, 256, algo="grid")[1], want)
+    # a single tight clump: the histogram predicts no gain, auto falls back to brute force
+    clump = np.concatenate([np.full((30000, 2), 0.5) + 1e-12 * rng.standard_normal((30000, 2)), [[0.0, 0.0], [1.0, 1.0]]])
+    e, got = grid_table(clump, 8, 1.0, 8192, algo="auto")
+    assert not e.knn_used_grid()
+    e2 = engine(clump, np.zeros(len(clump)))
+    e2.build_neighbors(8)
+    assert np.array_equal(got, e2.get_neighbors())
+    # non-finite coordinates never reach the grid
+    bad = rng.random((500, 2)); bad[17, 0] = np.inf
+    e3 = engine(bad, np.zeros(500))
+    e3.build_neighbors_grid(4, 0, None, "auto")
+    assert not e3.knn_used_grid()
+    with pytest.raises(_lib.NNGPError):
+        e3.build_neighbors_grid(4, 0, None, "grid")
+
+
+def test_knn_grid_row_ranges_assemble():
+    s, _ = synthetic(30000, 2, 9)
+    e, full = grid_table(s, 10, 1.0, 1024)
+    parts = []
+    for lo, hi in ((0, 700), (700, 11000), (11000, 30000)):
+        p = grid_table(s, 10, 1.0, 1024, lo, hi)[1]
+        assert np.array_equal(p[lo:hi], full[lo:hi])
+        assert ((p == full) | (p == _lib.ROW_UNSET)).all()
+        parts.append(p)
+    assert np.array_equal(np.maximum.reduce(parts), full)
+    b = grid_table(s, 10, 1.0, 1024, 5000, 6000, algo="brute")[1]
+    assert np.array_equal(b[5000:6000], full[5000:6000]) and (b[6000:] == _lib.ROW_UNSET).all()
+
+
+@pytest.mark.parametrize("n,D,m", [(200000, 2, 15), (120000, 3, 30)])
+def test_knn_grid_equals_brute_kernel_large(n, D, m):
+    s, _ = synthetic(n, D, 21)
+    e = engine(s, np.zeros(n))
+    e.build_neighbors(m)
+    want = e.get_neighbors()
+    e.build_neighbors_grid(m)          # defaults: auto, 8192 brute rows
+    assert e.knn_used_grid()
+    assert np.array_equal(e.get_neighbors(), want)
+
+
+def test_knn_plain_through_grid():
+    for D, n, k in ((2, 40000, 5), (3, 20000, 8), (1, 9000, 3)):
+        s, _ = synthetic(n, D, 70 + D)
+        e = engine(s, np.zeros(n))
+        idx = e.knn_plain(k)
+        assert (idx[:, 0] == np.arange(n)).all()
+        for i in list(range(0, n, n // 50)) + [n - 1]:
+            d2 = orc.np_dist2(s[i], s)
+            assert np.array_equal(idx[i], np.lexsort((np.arange(n), d2))[:k])
+
+
 # ---- stages 2-3 -----------------------------------------------------------------------------------
 CASES = [  # n, D, m, kernel
     (1000, 2, 10, "exponential"),   # cfg1
