@@ -51,16 +51,27 @@ __device__ __forceinline__ float t_fma(float a, float b, float c) { return fmaf(
 // that cost more issue slots than FP64-pipe slots; the arguments here are known to be positive,
 // finite and (for exp) non-positive, so the kernels below keep only the fast paths.
 
-constexpr int kExpTab = 64;  // exp(t) = 2^k * 2^(j/64) * e^r,  |r| <= ln2/128
+// exp(t) = 2^k * 2^(j/2^TB) * e^r, |r| <= ln2/2^(TB+1): a table of 2^TB entries in shared memory and a
+// polynomial whose degree shrinks as the table grows (truncation < 4e-17 in all three):
+//   TB = 11 (16 KB) cubic    -- the unrolled shapes, whose blocks have shared memory to spare
+//   TB =  8 ( 2 KB) quartic  -- the rolled (8, 4) shape: 2 blocks/SM must still fit
+//   TB =  6 (512 B) quintic  -- the rolled (16, 3) shape
+template <int TB> __host__ __device__ constexpr int exp_slot() { return TB == 11 ? 2 : TB == 8 ? 1 : 0; }
+__constant__ double kExpA[3] = {-64.0 / 0.6931471805599453094, -256.0 / 0.6931471805599453094,
+                                -2048.0 / 0.6931471805599453094};   // -2^TB / ln2
+// -(ln2 / 2^TB): one FMA computes k*c - u with a single rounding; the constant's own rounding error
+// (half an ulp) times k <= 2^TB u / ln2 stays below 1e-16 u, so no low-part correction is needed
+__constant__ double kExpB[3] = {-0.6931471805599453094 / 64.0, -0.6931471805599453094 / 256.0,
+                                -0.6931471805599453094 / 2048.0};
 
 // 64-bit constants of the covariance math.  Read as constant-bank operands (c[3][..]) they cost no
 // instruction; as literals ptxas re-materialises them (2 MOV each) inside the rolled build loop.
 __constant__ double kCovC[12] = {
     0.375,                     // 0  sqrt correction
-    -92.33248261689366,        // 1  -64/ln2
+    0.0,                       // 1  (unused)
     6755399441055744.0,        // 2  1.5 * 2^52 (round-to-nearest magic)
-    -0.01083042469326756,      // 3  -(ln2/64) high part
-    -2.9815858269852933e-12,   // 4  -(ln2/64) low part
+    0.0,                       // 3  (unused)
+    0.0,                       // 4  (unused)
     1.0 / 120.0,               // 5
     1.0 / 24.0,                // 6
     1.0 / 6.0,                 // 7
@@ -88,15 +99,14 @@ __device__ __forceinline__ float fast_sqrt(float d2)
     return fmaf(t1 * 0.5f, e, t1);
 }
 
-// 1/x for a positive finite pivot: MUFU.RCP64H seed + cubic correction
+// 1/x for a positive finite pivot: MUFU.RCP64H seed + one cubic correction (3 dependent FP64
+// operations: this sits on the pivot-to-pivot critical path of the elimination)
 __device__ __forceinline__ double fast_rcp(double x)
 {
     double r0;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r0) : "d"(x));
-    const double e = fma(-x, r0, 1.0);
-    const double r1 = fma(r0, fma(e, e, e), r0);
-    const double e1 = fma(-x, r1, 1.0);
-    return fma(r1, e1, r1);
+    const double e = fma(-x, r0, 1.0);   // |e| <= 2^-20 (the seed reads the high word only)
+    return fma(r0, fma(e, e, e), r0);    // r0 (1 + e + e^2): remainder e^3 < 2^-60
 }
 __device__ __forceinline__ float fast_rcp(float x)
 {
@@ -106,26 +116,30 @@ __device__ __forceinline__ float fast_rcp(float x)
     return fmaf(r0, e, r0);
 }
 
-// sigma2 * exp(-u) for u >= 0.  fp64: table of sigma2 * 2^(j/64) in shared memory (tab) + degree-5
-// polynomial on |r| <= ln2/128 (truncation 3e-17) -> 10 FP64 instructions instead of ~20 issue
-// slots more in exp().  u >= 708 (which includes the far-away sentinel rows) returns exactly 0.
+// sigma2 * exp(-u) for u >= 0.  fp64: table of sigma2 * 2^(j/2^TB) in shared memory (tab) + a short
+// polynomial -> 7 (TB = 11) to 9 (TB = 6) FP64 instructions.  u >= 708 (which includes the far-away
+// sentinel rows) returns exactly 0.
+template <int TB>
 __device__ __forceinline__ double scaled_exp_neg(double u, const double *tab, double /*sigma2*/)
 {
-    const double kd = fma(u, -92.33248261689366, 6755399441055744.0);
+    const double kd = fma(u, kExpA[exp_slot<TB>()], kCovC[2]);
     const int ki = __double2loint(kd);
-    const double kf = kd - 6755399441055744.0;           // = round(-u * 64/ln2)
-    double r = fma(kf, -0.01083042469326756, -u);
-    r = fma(kf, -2.9815858269852933e-12, r);
-    double q = fma(r, 1.0 / 120.0, 1.0 / 24.0);
-    q = fma(r, q, 1.0 / 6.0);
-    q = fma(r, q, 0.5);
+    const double kf = kd - kCovC[2];                      // = round(-u * 2^TB/ln2)
+    const double r = fma(kf, kExpB[exp_slot<TB>()], -u);
+    double q;
+    if (TB == 11) q = fma(r, 1.0 / 6.0, 0.5);
+    else {
+        q = TB == 8 ? fma(r, 1.0 / 24.0, 1.0 / 6.0) : fma(r, fma(r, 1.0 / 120.0, 1.0 / 24.0), 1.0 / 6.0);
+        q = fma(r, q, 0.5);
+    }
     q = fma(r, q, 1.0);
-    const double tv = tab[ki & (kExpTab - 1)];
+    const double tv = tab[ki & ((1 << TB) - 1)];
     const double p = fma(tv * r, q, tv);                  // tv * (1 + r*q)
-    const int hi = __double2hiint(p) + ((ki >> 6) << 20); // * 2^k
+    const int hi = __double2hiint(p) + ((ki >> TB) << 20); // * 2^k
     const double v = __hiloint2double(hi, __double2loint(p));
     return __double2hiint(u) >= 0x40862000 ? 0.0 : v;
 }
+template <int TB>
 __device__ __forceinline__ float scaled_exp_neg(float u, const float *, float sigma2)
 {
     const float kf = rintf(u * -1.4426950408889634f);
@@ -138,10 +152,10 @@ __device__ __forceinline__ float scaled_exp_neg(float u, const float *, float si
 }
 
 // sigma2 * rho(u), u = phi * distance (oracle: nngp_oracle.c corr()).
-template <typename T, int KERN>
+template <typename T, int KERN, int TB>
 __device__ __forceinline__ T cov_from_u(T u, const T *tab, T sigma2)
 {
-    const T e = scaled_exp_neg(u, tab, sigma2);
+    const T e = scaled_exp_neg<TB>(u, tab, sigma2);
     if (KERN == NNGP_EXPONENTIAL) return e;
     if (KERN == NNGP_MATERN32) return t_fma(u, e, e);
     return t_fma(u, t_fma(u, T(1.0 / 3.0), T(1)), T(1)) * e;
@@ -151,12 +165,12 @@ __device__ __forceinline__ T cov_from_u(T u, const T *tab, T sigma2)
 // instruction stream interleaves B dependency chains (the per-pair chain is ~20 dependent FP64
 // operations; with 3 resident warps per scheduler a single chain leaves the FP64 pipe idle).
 // In: x[b] = u_b^2 > 0.  Out: x[b] = sigma2 * rho(u_b).
-template <int KERN, int B>
+template <int KERN, int B, int TB>
 __device__ __forceinline__ void cov_batch(double (&x)[B], const double *tab, double)
 {
     double y0[B], t1[B], e[B], u[B], kd[B], r[B], qq[B], tv[B];
     int ki[B];
-    const double shift = kCovC[2], c5 = kCovC[5];  // second constants of two-constant FMAs: registers
+    const double shift = kCovC[2];  // second constant of a two-constant FMA: a register
 #pragma unroll
     for (int b = 0; b < B; ++b) asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y0[b]) : "d"(x[b]));
 #pragma unroll
@@ -170,21 +184,30 @@ __device__ __forceinline__ void cov_batch(double (&x)[B], const double *tab, dou
 #pragma unroll
     for (int b = 0; b < B; ++b) u[b] = fma(t1[b], y0[b], t1[b]);
 #pragma unroll
-    for (int b = 0; b < B; ++b) kd[b] = fma(u[b], kCovC[1], shift);
+    for (int b = 0; b < B; ++b) kd[b] = fma(u[b], kExpA[exp_slot<TB>()], shift);
 #pragma unroll
     for (int b = 0; b < B; ++b) { ki[b] = __double2loint(kd[b]); kd[b] = kd[b] - shift; }
 #pragma unroll
-    for (int b = 0; b < B; ++b) tv[b] = tab[ki[b] & (kExpTab - 1)];
+    for (int b = 0; b < B; ++b) tv[b] = tab[ki[b] & ((1 << TB) - 1)];
 #pragma unroll
-    for (int b = 0; b < B; ++b) r[b] = fma(kd[b], kCovC[3], -u[b]);
+    for (int b = 0; b < B; ++b) r[b] = fma(kd[b], kExpB[exp_slot<TB>()], -u[b]);
+    if (TB == 11) {
 #pragma unroll
-    for (int b = 0; b < B; ++b) r[b] = fma(kd[b], kCovC[4], r[b]);
+        for (int b = 0; b < B; ++b) qq[b] = fma(r[b], kCovC[7], 0.5);
+    } else {
+        if (TB == 8) {
 #pragma unroll
-    for (int b = 0; b < B; ++b) qq[b] = fma(r[b], c5, kCovC[6]);
+            for (int b = 0; b < B; ++b) qq[b] = fma(r[b], kCovC[6], kCovC[7]);
+        } else {
+            const double c5 = kCovC[5];
 #pragma unroll
-    for (int b = 0; b < B; ++b) qq[b] = fma(r[b], qq[b], kCovC[7]);
+            for (int b = 0; b < B; ++b) qq[b] = fma(r[b], c5, kCovC[6]);
 #pragma unroll
-    for (int b = 0; b < B; ++b) qq[b] = fma(r[b], qq[b], 0.5);
+            for (int b = 0; b < B; ++b) qq[b] = fma(r[b], qq[b], kCovC[7]);
+        }
+#pragma unroll
+        for (int b = 0; b < B; ++b) qq[b] = fma(r[b], qq[b], 0.5);
+    }
 #pragma unroll
     for (int b = 0; b < B; ++b) qq[b] = fma(r[b], qq[b], 1.0);
 #pragma unroll
@@ -193,7 +216,7 @@ __device__ __forceinline__ void cov_batch(double (&x)[B], const double *tab, dou
     for (int b = 0; b < B; ++b) r[b] = fma(r[b], qq[b], tv[b]);
 #pragma unroll
     for (int b = 0; b < B; ++b) {
-        const int hi = __double2hiint(r[b]) + ((ki[b] >> 6) << 20);
+        const int hi = __double2hiint(r[b]) + ((ki[b] >> TB) << 20);
         const double v = __hiloint2double(hi, __double2loint(r[b]));
         e[b] = __double2hiint(u[b]) >= 0x40862000 ? 0.0 : v;
     }
@@ -204,11 +227,11 @@ __device__ __forceinline__ void cov_batch(double (&x)[B], const double *tab, dou
         else x[b] = fma(u[b], fma(u[b], kCovC[8], 1.0), 1.0) * e[b];
     }
 }
-template <int KERN, int B>
+template <int KERN, int B, int TB>
 __device__ __forceinline__ void cov_batch(float (&x)[B], const float *tab, float sigma2)
 {
 #pragma unroll
-    for (int b = 0; b < B; ++b) x[b] = cov_from_u<float, KERN>(fast_sqrt(x[b]), tab, sigma2);
+    for (int b = 0; b < B; ++b) x[b] = cov_from_u<float, KERN, TB>(fast_sqrt(x[b]), tab, sigma2);
 }
 
 // far-away sentinel for padded rows: every covariance with it underflows to exactly 0
@@ -282,14 +305,22 @@ struct WarpSmem {
 };
 
 // block-shared part: exp table + the launch's pair list (one packed word per pair)
-template <int P, int BUILD>
-__host__ __device__ constexpr size_t block_smem() { return kExpTab * sizeof(double) + (BUILD == 1 ? (size_t(P) * (P - 1) / 2 + 64) * 8 : 0); }
+template <int G, int BUILD>
+__host__ __device__ constexpr int exp_tab_bits() { return BUILD == 0 ? 11 : (G == 16 ? 6 : 8); }
+// fp32 has no table; the region doubles as the final reduction's scratch (kThreads x 3 doubles)
+template <typename T, int G, int BUILD>
+__host__ __device__ constexpr size_t exp_tab_bytes()
+{
+    return sizeof(T) == 8 && (sizeof(double) << exp_tab_bits<G, BUILD>()) > 3072 ? (sizeof(double) << exp_tab_bits<G, BUILD>()) : 3072;
+}
+template <typename T, int G, int R, int BUILD>
+__host__ __device__ constexpr size_t block_smem() { return exp_tab_bytes<T, G, BUILD>() + (BUILD == 1 ? (size_t(G * R) * (G * R - 1) / 2 + 64) * 8 : 0); }
 
 // dynamic shared memory needed by one block
 template <typename T, int G, int R, bool DIM3, int BUILD>
 constexpr size_t smem_bytes(bool emit)
 {
-    return block_smem<G * R, BUILD>() + size_t(kWarps) * WarpSmem<T, G, R, DIM3, BUILD>::total(emit);
+    return block_smem<T, G, R, BUILD>() + size_t(kWarps) * WarpSmem<T, G, R, DIM3, BUILD>::total(emit);
 }
 
 template <typename T, int G, int R, int KERN, bool DIM3, int MINB, int BUILD>
@@ -307,8 +338,8 @@ __global__ void __launch_bounds__(kThreads, MINB) fused_loglik_kernel(const Eval
     const int g = lane / G;  // location slot inside the warp
 
     T *exp_tab = reinterpret_cast<T *>(smem_raw);  // sigma2 * 2^(j/64) (fp64 path only)
-    uint2 *pair_lut = reinterpret_cast<uint2 *>(smem_raw + kExpTab * sizeof(double));
-    unsigned char *wbase = smem_raw + block_smem<P, BUILD>() + size_t(warp) * WS::total(a.emit != 0);
+    uint2 *pair_lut = reinterpret_cast<uint2 *>(smem_raw + exp_tab_bytes<T, G, BUILD>());
+    unsigned char *wbase = smem_raw + block_smem<T, G, R, BUILD>() + size_t(warp) * WS::total(a.emit != 0);
     unsigned char *recbuf = wbase + g * WS::rec_stride;  // this location's records (16-byte aligned)
     double *e2buf = reinterpret_cast<double *>(wbase + WS::rec);
     int *idxbuf = reinterpret_cast<int *>(wbase + WS::rec + WS::e2) + lane;          // [s * 32]
@@ -323,7 +354,9 @@ __global__ void __launch_bounds__(kThreads, MINB) fused_loglik_kernel(const Eval
     const double phi = prm[1];
     const double diag0 = prm[0] + prm[2];
     const int m = a.m;
-    if (threadIdx.x < kExpTab) exp_tab[threadIdx.x] = T(prm[0] * exp2(double(threadIdx.x) / kExpTab));
+    constexpr int TB = exp_tab_bits<G, BUILD>();
+    if constexpr (sizeof(T) == 8)
+        for (int k = threadIdx.x; k < (1 << TB); k += kThreads) exp_tab[k] = T(prm[0] * exp2(double(k) / (1 << TB)));
     accbuf[0] = 0.0; accbuf[32] = 0.0; accbuf[64] = 0.0;  // sum log F, sum r^2/F, n_bad: rarely touched,
                                                             // kept out of the register file
     // The launch's pair list: rows in play are the m neighbour rows and the location's own row P-1
@@ -479,7 +512,7 @@ __global__ void __launch_bounds__(kThreads, MINB) fused_loglik_kernel(const Eval
                         d2[b] = t_fma(dy, dy, t_fma(dx, dx, tiny_seed<T>()));
                         if constexpr (DIM3) { const T dz = pa.z - pb.z; d2[b] = t_fma(dz, dz, d2[b]); }
                     }
-                    cov_batch<KERN, CB>(d2, exp_tab, sigma2);
+                    cov_batch<KERN, CB, TB>(d2, exp_tab, sigma2);
     #pragma unroll
                     for (int b = 0; b < CB; ++b) *reinterpret_cast<T *>(tb + eoff[b]) = d2[b];
                 }
@@ -521,7 +554,7 @@ __global__ void __launch_bounds__(kThreads, MINB) fused_loglik_kernel(const Eval
                     d2[b] = t_fma(dy, dy, t_fma(dx, dx, tiny_seed<T>()));
                     if constexpr (DIM3) { const T dz = rz[s] - cj.z; d2[b] = t_fma(dz, dz, d2[b]); }
                 }
-                cov_batch<KERN, CB>(d2, exp_tab, sigma2);
+                cov_batch<KERN, CB, TB>(d2, exp_tab, sigma2);
 #pragma unroll
                 for (int b = 0; b < CB; ++b) {
                     if (t0 + b < NP) {

@@ -48,7 +48,7 @@ class NeighborSets:
 
 class NNGP(object):
     def __init__(self, t, y, eps, refType, m, cov, *, dtype="float64", device=None, neighbors=None,
-                 group=None):
+                 group=None, knn="auto"):
         self.t = t  # ordinates
         self.y = y  # abscissae
         self.eps = eps  # measurement uncertainties in y
@@ -57,6 +57,9 @@ class NNGP(object):
         self.cov = cov  # covariance of the parent GP: kernel spec (see pynngp_b200.kernels)
 
         self._kernel: Kernel = _parse_cov(cov)
+        if knn not in ("auto", "grid", "brute"):
+            raise ValueError("knn must be 'auto', 'grid' or 'brute'")
+        self._knn = knn  # stage-1 algorithm: cell-grid search (bit-identical) unless the data defeats it
         self._group = group
         self._rank, self._world = _dist.get_world(group)
         if device is None:
@@ -102,7 +105,11 @@ class NNGP(object):
                               self._y2d.shape)
         self._eps2 = None if not np.any(eps) else np.ascontiguousarray(eps * eps)
         self._coords = s
+        import time
+
+        t0 = time.perf_counter()
         self._set_column(0)
+        self._timings["upload_s"] = time.perf_counter() - t0
         lo, hi = _dist.shard_bounds(n, self._rank, self._world)
         self._engine.set_shard(lo, hi)
         self._shard = (lo, hi)
@@ -131,22 +138,47 @@ class NNGP(object):
         if neighbors is not None:
             eng.set_neighbors(neighbors)
         elif self._world == 1:
-            eng.build_neighbors(self.m)
+            eng.build_neighbors_grid(self.m, 0, eng.n, self._knn)
         else:
             import torch
 
-            off, stride = _dist.knn_tile_split(self._rank, self._world)
-            eng.build_neighbors(self.m, off, stride)
+            if self._knn == "brute":
+                # quadratic work grows with i: tiles dealt round-robin from the heavy end
+                off, stride = _dist.knn_tile_split(self._rank, self._world)
+                eng.build_neighbors(self.m, off, stride)
+            else:
+                # grid search is ~uniform per row: every rank builds the rows of its own shard
+                eng.build_neighbors_grid(self.m, self._shard[0], self._shard[1], self._knn)
+            self._timings["knn_local_s"] = time.perf_counter() - t0
             view = _dist.DevicePtrView(eng.neighbors_device_ptr(), (eng.n, eng.m), "<i4")
             tab = torch.as_tensor(view, device=f"cuda:{eng.device}")
-            _dist.assemble_table_max(tab, self._group)
+            _dist.assemble_table_max(tab, self._group)  # unset rows hold -2
             torch.cuda.synchronize(eng.device)
         self._timings["knn_s"] = time.perf_counter() - t0
-        self._table = eng.get_neighbors()
-        self.Ns = NeighborSets(self._table)
+        self._table_host = None if neighbors is None else np.ascontiguousarray(neighbors, dtype=np.int32)
+        self._Ns = None
+
+    @property
+    def _table(self):
+        """(n, m) int32 neighbour table on the host; downloaded from the device the first time it is
+        read (the likelihood itself never needs it on the host)."""
+        if self._table_host is None:
+            self._table_host = self._engine.get_neighbors()
+        return self._table_host
+
+    @property
+    def Ns(self):
+        """The reference's list of neighbour index arrays (nngp.py:49-62)."""
+        if self._Ns is None:
+            self._Ns = NeighborSets(self._table)
+        return self._Ns
+
+    @property
+    def Nt(self):
+        return self.Ns  # nngp.py:65-67: the same object
 
     def _make_t_neighbor_sets(self):
-        self.Nt = self.Ns  # nngp.py:65-67
+        pass  # nngp.py:65-67 for S = T: Nt is Ns (see the property above)
 
     @property
     def ws(self):

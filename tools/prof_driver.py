@@ -17,7 +17,7 @@ if len(sys.argv) > 4:
 s, y = synthetic(c["n"], c["D"], c["seed"])
 e = _lib.Engine(0, dtype)
 e.set_data(s, y)
-e.build_neighbors(c["m"])
+e.build_neighbors_grid(c["m"])
 kid = {"exponential": 0, "matern32": 1, "matern52": 2}[c["kernel"]]
 prm = np.array([PARAMS["sigma2"], PARAMS["phi"], PARAMS["tau2"], 0.0])
 for _ in range(reps):

@@ -28,7 +28,7 @@ for dtype in dtypes:
     if table is None:
         t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
         import time
-        tt = time.perf_counter(); e.build_neighbors(c["m"]); print(f"knn build {time.perf_counter()-tt:.3f}s", flush=True)
+        tt = time.perf_counter(); e.build_neighbors_grid(c["m"]); print(f"knn build {time.perf_counter()-tt:.3f}s", flush=True)
         table = e.get_neighbors()
     else:
         e.set_neighbors(table)
