@@ -299,7 +299,10 @@ struct WarpSmem {
     static constexpr size_t idx = size_t(R) * 32 * sizeof(int);          // next group's neighbour indices
     static constexpr size_t acc = size_t(3) * 32 * sizeof(double);       // per-lane partial sums
     static constexpr size_t tile = BUILD == 1 ? (size_t(W) * tile_stride<P>() * sizeof(T) + 15) / 16 * 16 : 0;  // pair-indexed tile
-    static constexpr size_t stage = size_t(W) * stage_stride;                      // scaled coordinates
+    // scaled coordinates during the build; the elimination's two column buffers afterwards
+    static constexpr int col_stride = P + 2;  // elements per location: P column entries, w_k, pad (distinct banks per group)
+    static constexpr size_t colbuf = size_t(2) * W * col_stride * sizeof(T);
+    static constexpr size_t stage = (size_t(W) * stage_stride > colbuf ? size_t(W) * stage_stride : colbuf);
     static constexpr size_t dump = size_t(P) * P * sizeof(T);            // emit only: one location's factor
     __host__ __device__ static constexpr size_t total(bool emit) { return rec + e2 + idx + acc + tile + stage + (emit ? dump : 0); }
 };
@@ -307,14 +310,17 @@ struct WarpSmem {
 // block-shared part: exp table + the launch's pair list (one packed word per pair)
 template <int G, int BUILD>
 __host__ __device__ constexpr int exp_tab_bits() { return BUILD == 0 ? 11 : (G == 16 ? 6 : 8); }
-// fp32 has no table; the region doubles as the final reduction's scratch (kThreads x 3 doubles)
+// pairs evaluated in lock step by one lane: 8 in the rolled (8, 4) build, whose loop is bound by the
+// latency of its dependent shared-memory reads (pair list -> coordinates -> exp table)
+template <int G, int BUILD>
+__host__ __device__ constexpr int cov_batch_size() { return BUILD == 1 && G == 8 ? 8 : 4; }
 template <typename T, int G, int BUILD>
-__host__ __device__ constexpr size_t exp_tab_bytes()
-{
-    return sizeof(T) == 8 && (sizeof(double) << exp_tab_bits<G, BUILD>()) > 3072 ? (sizeof(double) << exp_tab_bits<G, BUILD>()) : 3072;
-}
+__host__ __device__ constexpr size_t exp_tab_bytes() { return sizeof(T) == 8 ? (sizeof(double) << exp_tab_bits<G, BUILD>()) : 16; }  // fp32: no table
 template <typename T, int G, int R, int BUILD>
-__host__ __device__ constexpr size_t block_smem() { return exp_tab_bytes<T, G, BUILD>() + (BUILD == 1 ? (size_t(G * R) * (G * R - 1) / 2 + 64) * 8 : 0); }
+__host__ __device__ constexpr size_t block_smem()
+{
+    return exp_tab_bytes<T, G, BUILD>() + (BUILD == 1 ? (size_t(G * R) * (G * R - 1) / 2 + G * cov_batch_size<G, BUILD>()) * 8 : 0);
+}
 
 // dynamic shared memory needed by one block
 template <typename T, int G, int R, bool DIM3, int BUILD>
@@ -323,7 +329,14 @@ constexpr size_t smem_bytes(bool emit)
     return block_smem<T, G, R, BUILD>() + size_t(kWarps) * WarpSmem<T, G, R, DIM3, BUILD>::total(emit);
 }
 
-template <typename T, int G, int R, int KERN, bool DIM3, int MINB, int BUILD>
+template <typename T> struct Pair2;
+template <> struct Pair2<double> { using type = double2; };
+template <> struct Pair2<float> { using type = float2; };
+
+// ELIM = 0: pivot-column entries travel by width-G warp shuffles.  ELIM = 1: the lanes publish the
+// column in shared memory once per pivot and read it back as broadcast 2-element loads -- a quarter
+// of the instructions the 64-bit shuffles (two SHFL plus their register moves each) cost.
+template <typename T, int G, int R, int KERN, bool DIM3, int MINB, int BUILD, int ELIM>
 __global__ void __launch_bounds__(kThreads, MINB) fused_loglik_kernel(const EvalArgs a)
 {
     constexpr int P = G * R;   // rows of the augmented matrix
@@ -348,6 +361,9 @@ __global__ void __launch_bounds__(kThreads, MINB) fused_loglik_kernel(const Eval
     T *tile = tile_w + g * tile_stride<P>();  // this location's covariance entries
     Pt *stage = reinterpret_cast<Pt *>(wbase + WS::rec + WS::e2 + WS::idx + WS::acc + WS::tile + g * WS::stage_stride);
     T *dump = reinterpret_cast<T *>(wbase + WS::rec + WS::e2 + WS::idx + WS::acc + WS::tile + WS::stage);
+    // column buffers of the elimination: alias the staged coordinates (dead once the build is done)
+    T *colw = reinterpret_cast<T *>(wbase + WS::rec + WS::e2 + WS::idx + WS::acc + WS::tile);
+    T *col_even = colw + g * WS::col_stride, *col_odd = colw + (W + g) * WS::col_stride;
 
     const double *prm = a.params + size_t(blockIdx.y) * NNGP_NPARAM;
     const T sigma2 = T(prm[0]);
@@ -363,7 +379,7 @@ __global__ void __launch_bounds__(kThreads, MINB) fused_loglik_kernel(const Eval
     // (rows m .. P-2 are identity padding: their entries stay at the zero the tile is filled with).
     // Pair t -> packed {row a, column b, tile offset a(a-1)/2 + b}; lanes walk the list with stride G,
     // which splits the build evenly (m = 15: 30 pairs per lane) whatever the row-owner layout is.
-    constexpr int CB = 4;  // pairs evaluated in lock step by one lane
+    constexpr int CB = cov_batch_size<G, BUILD>();  // pairs evaluated in lock step by one lane
     const int rows_in_play = m + 1;
     const int npairs = rows_in_play * (rows_in_play - 1) / 2;
     const int nbatch = (npairs + G * CB - 1) / (G * CB);  // build-loop trips; the list is padded to it
@@ -594,6 +610,53 @@ __global__ void __launch_bounds__(kThreads, MINB) fused_loglik_kernel(const Eval
         // ---- stage 3: LDL^T elimination with the right-hand side carried along -----------------
         bool bad = false;
         T Flast = T(1), rlast = T(0);
+        if constexpr (ELIM == 1) {
+            using T2 = typename Pair2<T>::type;
+#pragma unroll
+            for (int k = 0; k < P; ++k) {
+                T *col = (k & 1) ? col_odd : col_even;
+                // publish column k (this lane's rows from the pivot's row block on) and w_k; two
+                // buffers alternate, so one __syncwarp per pivot orders writes against earlier reads
+#pragma unroll
+                for (int s = 0; s < R; ++s)
+                    if (s * G + G - 1 >= k) col[s * G + q] = A[s][k];
+                if (q == k % G) col[P] = w[k / G];
+                __syncwarp();
+                const T Dk = col[k], wk = col[P];
+                bad |= !(Dk > T(0));
+                if (k == P - 1) {
+                    Flast = Dk;
+                    rlast = wk;
+                } else {
+                    const T inv = fast_rcp(Dk);
+                    T l[R];
+#pragma unroll
+                    for (int s = 0; s < R; ++s) {
+                        if (s * G + G - 1 > k) {
+                            l[s] = A[s][k] * inv;
+                            w[s] = t_fma(-l[s], wk, w[s]);
+                        }
+                    }
+#pragma unroll
+                    for (int j0 = 0; j0 < P; j0 += 2) {
+                        if (j0 + 1 > k) {
+                            const T2 uu = *reinterpret_cast<const T2 *>(col + j0);  // broadcast inside the group
+                            if (j0 > k) {
+#pragma unroll
+                                for (int s = 0; s < R; ++s)
+                                    if (s * G + G - 1 >= j0) A[s][j0] = t_fma(-l[s], uu.x, A[s][j0]);
+                            }
+#pragma unroll
+                            for (int s = 0; s < R; ++s)
+                                if (s * G + G - 1 >= j0 + 1) A[s][j0 + 1] = t_fma(-l[s], uu.y, A[s][j0 + 1]);
+                        }
+                    }
+#pragma unroll
+                    for (int s = 0; s < R; ++s)
+                        if (s * G + G - 1 > k) A[s][k] = l[s];  // unit-lower factor (emit path)
+                }
+            }
+        } else {
 #pragma unroll
         for (int k = 0; k < P; ++k) {
             const T Dk = grp_bcast<T, G>(A[k / G][k], k % G);
@@ -628,6 +691,8 @@ __global__ void __launch_bounds__(kThreads, MINB) fused_loglik_kernel(const Eval
                 for (int s = 0; s < R; ++s)
                     if (s * G + G - 1 > k) A[s][k] = l[s];  // unit-lower factor (emit path)
             }
+        }
+
         }
 
         if (live && q == 0) {
@@ -728,10 +793,10 @@ __global__ void __launch_bounds__(kThreads, MINB) fused_loglik_kernel(const Eval
 }
 
 // ---- host-side dispatch of one (T, KERN) family -------------------------------------------------
-template <typename T, int G, int R, int KERN, bool DIM3, int MINB, int BUILD>
+template <typename T, int G, int R, int KERN, bool DIM3, int MINB, int BUILD, int ELIM>
 cudaError_t launch_one(const EvalArgs &a, int K, int grid_x, cudaStream_t stream)
 {
-    auto kern = fused_loglik_kernel<T, G, R, KERN, DIM3, MINB, BUILD>;
+    auto kern = fused_loglik_kernel<T, G, R, KERN, DIM3, MINB, BUILD, ELIM>;
     const size_t smem = smem_bytes<T, G, R, DIM3, BUILD>(a.emit != 0);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
@@ -742,10 +807,10 @@ cudaError_t launch_one(const EvalArgs &a, int K, int grid_x, cudaStream_t stream
     return cudaGetLastError();
 }
 
-template <typename T, int G, int R, int KERN, bool DIM3, int MINB, int BUILD>
+template <typename T, int G, int R, int KERN, bool DIM3, int MINB, int BUILD, int ELIM>
 int blocks_per_sm()
 {
-    auto kern = fused_loglik_kernel<T, G, R, KERN, DIM3, MINB, BUILD>;
+    auto kern = fused_loglik_kernel<T, G, R, KERN, DIM3, MINB, BUILD, ELIM>;
     int nb = 0;
     const size_t smem = smem_bytes<T, G, R, DIM3, BUILD>(false);
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -764,29 +829,37 @@ struct ShapeInfo {
     int loc_per_warp;
 };
 
+constexpr int kElim = 1;  // production elimination variant (see fused_loglik_kernel)
+
 template <typename T, int KERN>
 struct Launcher {
     const EvalArgs &a;
     int K, grid_x;
     cudaStream_t stream;
-    template <int G, int R, bool DIM3, int MINB, int BUILD>
-    cudaError_t run() const { return launch_one<T, G, R, KERN, DIM3, MINB, BUILD>(a, K, grid_x, stream); }
+    template <int G, int R, bool DIM3, int MINB, int BUILD, int ELIM = kElim>
+    cudaError_t run() const { return launch_one<T, G, R, KERN, DIM3, MINB, BUILD, ELIM>(a, K, grid_x, stream); }
 };
 template <typename T, int KERN>
 struct Describer {
-    template <int G, int R, bool DIM3, int MINB, int BUILD>
-    ShapeInfo run() const { return ShapeInfo{blocks_per_sm<T, G, R, KERN, DIM3, MINB, BUILD>(), 32 / G}; }
+    template <int G, int R, bool DIM3, int MINB, int BUILD, int ELIM = kElim>
+    ShapeInfo run() const { return ShapeInfo{blocks_per_sm<T, G, R, KERN, DIM3, MINB, BUILD, ELIM>(), 32 / G}; }
 };
 
 template <typename T, bool DIM3, typename F>
 auto dispatch_shape(int m, const F &f)
 {
     constexpr bool F64 = sizeof(T) == 8;
-#ifdef NNGP_TUNE  // development knob for the m <= 15 shape: NNGP_TUNE_SHAPE = 4x4r | 4x4u | 4x4u3
+#ifdef NNGP_TUNE  // development knobs: NNGP_TUNE_ELIM = 0 selects the shuffle elimination
+    if (const char *e = getenv("NNGP_TUNE_ELIM"); e && atoi(e) == 0) {
+        if (m <= 7) return f.template run<4, 2, DIM3, 4, 0, 0>();
+        if (m <= 15) return f.template run<4, 4, DIM3, (F64 ? 3 : 4), 0, 0>();
+        if (m <= 31) return f.template run<8, 4, DIM3, (F64 ? 2 : 4), 1, 0>();
+        return f.template run<16, 3, DIM3, (F64 ? 2 : 4), 1, 0>();
+    }
     if (const char *e = getenv("NNGP_TUNE_SHAPE"); e && m > 7 && m <= 15 && !DIM3) {
         if (!strcmp(e, "4x4r")) return f.template run<4, 4, DIM3, 2, 1>();
-        if (!strcmp(e, "4x4u")) return f.template run<4, 4, DIM3, 2, 0>();
-        if (!strcmp(e, "4x4u3")) return f.template run<4, 4, DIM3, 3, 0>();
+        if (!strcmp(e, "4x4u2")) return f.template run<4, 4, DIM3, 2, 0>();
+        if (!strcmp(e, "8x2u")) return f.template run<8, 2, DIM3, 4, 0>();
     }
 #endif
     if (m <= 7) return f.template run<4, 2, DIM3, 4, 0>();
