@@ -85,6 +85,11 @@ int nngp_build_neighbors(nngp_handle *h, int m, int tile_offset, int tile_stride
  * histogram predicts more work than brute force; NNGP_KNN_GRID / NNGP_KNN_BRUTE force one. */
 enum { NNGP_KNN_AUTO = 0, NNGP_KNN_GRID = 1, NNGP_KNN_BRUTE = 2 };
 int nngp_build_neighbors_grid(nngp_handle *h, int m, int64_t row_lo, int64_t row_hi, int algo);
+/* Same search with the candidates of row i restricted to j < min(i, cand_cap).  With the n reference
+ * sites in rows [0, n) and q prediction sites appended as rows [n, n + q), row_lo = cand_cap = n gives
+ * every new site its m nearest REFERENCE sites (the neighbour sets kriging conditions on; the step after
+ * the path); nngp_factors over the same rows then returns the kriging weights and variances. */
+int nngp_build_neighbors_capped(nngp_handle *h, int m, int64_t row_lo, int64_t row_hi, int64_t cand_cap, int algo);
 /* Grid search knobs: cells hold lambda_scale * (m + 2 sqrt m) / unit-ball-volume usable points
  * (default 1.0); rows below brute_rows (default 8192) always use brute force. */
 int nngp_set_knn_tuning(nngp_handle *h, double lambda_scale, int64_t brute_rows);
@@ -93,6 +98,8 @@ int nngp_knn_used_grid(const nngp_handle *h);
 /* Injects a table (n x m int32 row-major, -1 padded; valid entries first in each row). */
 int nngp_set_neighbors(nngp_handle *h, const int32_t *idx, int m);
 int nngp_get_neighbors(nngp_handle *h, int32_t *out);
+/* Rows [i0, i1) of the table only: out is (i1-i0) x m int32. */
+int nngp_get_neighbor_rows(nngp_handle *h, int64_t i0, int64_t i1, int32_t *out);
 /* Plain k-NN over all rows, the query itself included (no ordering constraint), same (d2, j) order;
  * out: n x k int32 on the host.  Replaces the neighbour search inside _init_ws, nngp.py:45-47
  * (KNeighborsRegressor(5).fit(t, y).predict(s): the mean of y over these rows is `ws`). */

@@ -34,10 +34,12 @@ SIGNATURES = {
     "nngp_set_shard": (ctypes.c_int, [_handle_p, ctypes.c_int64, ctypes.c_int64]),
     "nngp_build_neighbors": (ctypes.c_int, [_handle_p, ctypes.c_int, ctypes.c_int, ctypes.c_int]),
     "nngp_build_neighbors_grid": (ctypes.c_int, [_handle_p, ctypes.c_int, ctypes.c_int64, ctypes.c_int64, ctypes.c_int]),
+    "nngp_build_neighbors_capped": (ctypes.c_int, [_handle_p, ctypes.c_int, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, ctypes.c_int]),
     "nngp_set_knn_tuning": (ctypes.c_int, [_handle_p, ctypes.c_double, ctypes.c_int64]),
     "nngp_knn_used_grid": (ctypes.c_int, [_handle_p]),
     "nngp_set_neighbors": (ctypes.c_int, [_handle_p, _c_int32_p, ctypes.c_int]),
     "nngp_get_neighbors": (ctypes.c_int, [_handle_p, _c_int32_p]),
+    "nngp_get_neighbor_rows": (ctypes.c_int, [_handle_p, ctypes.c_int64, ctypes.c_int64, _c_int32_p]),
     "nngp_knn_plain": (ctypes.c_int, [_handle_p, ctypes.c_int, _c_int32_p]),
     "nngp_neighbors_device_ptr": (ctypes.c_void_p, [_handle_p]),
     "nngp_loglik": (ctypes.c_int, [_handle_p, ctypes.c_int, _c_double_p, ctypes.c_int, _c_double_p]),
@@ -148,6 +150,14 @@ class Engine:
                     "nngp_build_neighbors_grid")
         self.m = int(m)
 
+    def build_neighbors_capped(self, m, row_lo, row_hi, cand_cap, algo="auto"):
+        """Rows [row_lo, row_hi): the m nearest j < min(i, cand_cap) (prediction sites appended after the
+        cand_cap reference sites get reference-only neighbours)."""
+        code = {"auto": 0, "grid": 1, "brute": 2}[algo]
+        self._check(self._lib.nngp_build_neighbors_capped(self._h, int(m), int(row_lo), int(row_hi), int(cand_cap), code),
+                    "nngp_build_neighbors_capped")
+        self.m = int(m)
+
     def set_knn_tuning(self, lambda_scale=1.0, brute_rows=8192):
         self._check(self._lib.nngp_set_knn_tuning(self._h, float(lambda_scale), int(brute_rows)), "nngp_set_knn_tuning")
 
@@ -165,6 +175,12 @@ class Engine:
     def get_neighbors(self):
         out = np.empty((self.n, self.m), dtype=np.int32)
         self._check(self._lib.nngp_get_neighbors(self._h, out.ctypes.data_as(_c_int32_p)), "nngp_get_neighbors")
+        return out
+
+    def get_neighbor_rows(self, i0, i1):
+        out = np.empty((int(i1) - int(i0), self.m), dtype=np.int32)
+        self._check(self._lib.nngp_get_neighbor_rows(self._h, int(i0), int(i1), out.ctypes.data_as(_c_int32_p)),
+                    "nngp_get_neighbor_rows")
         return out
 
     def knn_plain(self, k):

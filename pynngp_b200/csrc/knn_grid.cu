@@ -25,6 +25,7 @@
 // n = 1e6, m = 15 (brute force: 5e11).  Clustered data only costs time, never exactness; when the
 // top-level histogram predicts more work than brute force the caller is told to use that instead.
 #include <math.h>
+#include <stdint.h>
 
 #include <algorithm>
 
@@ -51,16 +52,17 @@ __device__ __forceinline__ int cell_index(const GridSpec &gs, double x, double y
     return (cz * gs.G[1] + cy) * gs.G[0] + cx;
 }
 
-// cell of every point 0 .. N-1; histogram of all points and of the level's queries [qlo, qhi)
+// cell of every point 0 .. N-1; histogram of the candidate points 0 .. ncand-1 and of the level's
+// queries [qlo, qhi)
 template <bool DIM3>
-__global__ void cell_count_kernel(const double4 *__restrict__ pts, int N, GridSpec gs, int qlo, int qhi,
+__global__ void cell_count_kernel(const double4 *__restrict__ pts, int N, int ncand, GridSpec gs, int qlo, int qhi,
                                   int *__restrict__ cell_of, int *counts, int *qcounts)
 {
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x) {
         const double4 p = pts[i];
         const int c = cell_index(gs, p.x, p.y, DIM3 ? p.z : gs.lo[2]);
         cell_of[i] = c;
-        atomicAdd(counts + c, 1);
+        if (i < ncand) atomicAdd(counts + c, 1);
         if (i >= qlo && i < qhi) atomicAdd(qcounts + c, 1);
     }
 }
@@ -135,15 +137,17 @@ __global__ void __launch_bounds__(1024) scan_cells_kernel(const int *counts, int
 
 // records and query ids into cell order (the order inside a cell is arbitrary: the search compares
 // (d2, j), so it does not matter)
-__global__ void scatter_kernel(const double4 *__restrict__ pts, int N, const int *__restrict__ cell_of, int qlo,
-                               int qhi, int *cursor, int *qcursor, double4 *__restrict__ sorted,
+__global__ void scatter_kernel(const double4 *__restrict__ pts, int N, int ncand, const int *__restrict__ cell_of,
+                               int qlo, int qhi, int *cursor, int *qcursor, double4 *__restrict__ sorted,
                                int *__restrict__ qlist)
 {
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x) {
         const int c = cell_of[i];
-        double4 p = pts[i];
-        p.w = __hiloint2double(0, i);  // the record's y value is not needed here: carry the index
-        sorted[atomicAdd(cursor + c, 1)] = p;
+        if (i < ncand) {
+            double4 p = pts[i];
+            p.w = __hiloint2double(0, i);  // the record's y value is not needed here: carry the index
+            sorted[atomicAdd(cursor + c, 1)] = p;
+        }
         if (i >= qlo && i < qhi) qlist[atomicAdd(qcursor + c, 1)] = i;
     }
 }
@@ -186,7 +190,7 @@ __global__ void __launch_bounds__(TQ) knn_grid_query_kernel(const double4 *__res
                                                             const int *__restrict__ starts,
                                                             const int *__restrict__ cell_of,
                                                             const int *__restrict__ qlist, int nq, GridSpec gs, int m,
-                                                            int32_t *__restrict__ out)
+                                                            int cand_cap, int32_t *__restrict__ out)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double *keys_all = reinterpret_cast<double *>(smem_raw);
@@ -197,6 +201,7 @@ __global__ void __launch_bounds__(TQ) knn_grid_query_kernel(const double4 *__res
     const double4 q = pts[i];
     const double qx = q.x, qy = q.y, qz = q.z;
     const int Gx = gs.G[0], Gy = gs.G[1], Gz = gs.G[2];
+    const int jlim = i < cand_cap ? i : cand_cap;  // ORDERED: candidates are j < min(i, cand_cap)
     int c = cell_of[i];  // as assigned by cell_count_kernel: query and candidates use one assignment
     const int cx = c % Gx;
     c /= Gx;
@@ -222,7 +227,7 @@ __global__ void __launch_bounds__(TQ) knn_grid_query_kernel(const double4 *__res
                 const double dz = qz - b.x;
                 d = __dadd_rn(d, __dmul_rn(dz, dz));
             }
-            if ((!ORDERED || j < i) && top.accepts(d, j)) top.insert(d, j);
+            if ((!ORDERED || j < jlim) && top.accepts(d, j)) top.insert(d, j);
         }
     };
 
@@ -349,8 +354,8 @@ cudaError_t launch_fill_i32(nngp_handle *h, int32_t *p, int64_t count, int32_t v
 // from the brute-force kernel.  ordered = false: one level over all n points, the query itself
 // included.  *used = 0 (and nothing computed) when the data does not suit a grid and force == 0:
 // non-finite coordinates, or a histogram that predicts more work than brute force.
-cudaError_t launch_knn_grid(nngp_handle *h, bool ordered, int m, int64_t row_lo, int64_t row_hi, int32_t *table,
-                            cudaStream_t stream, int force, int *used)
+cudaError_t launch_knn_grid(nngp_handle *h, bool ordered, int m, int64_t row_lo, int64_t row_hi, int64_t cand_cap,
+                            int32_t *table, cudaStream_t stream, int force, int *used)
 {
     using namespace nngp_grid;
     *used = 0;
@@ -397,7 +402,7 @@ cudaError_t launch_knn_grid(nngp_handle *h, bool ordered, int m, int64_t row_lo,
     int cap_cells = 0;
     if (any_level) {
         for (int l = 0; l < nlev; ++l)
-            cap_cells = std::max(cap_cells, make_grid(h, double(ordered ? lev[l].a : n), lambda, max_cells).ncell);
+            cap_cells = std::max(cap_cells, make_grid(h, double(ordered ? std::min(lev[l].a, cand_cap) : n), lambda, max_cells).ncell);
         GRID_TRY(cudaMalloc(&sc.sorted, sizeof(double4) * size_t(n)));
         GRID_TRY(cudaMalloc(&sc.cell_of, sizeof(int) * size_t(n)));
         GRID_TRY(cudaMalloc(&sc.qlist, sizeof(int) * size_t(n)));
@@ -420,14 +425,15 @@ cudaError_t launch_knn_grid(nngp_handle *h, bool ordered, int m, int64_t row_lo,
         const int64_t qlo = std::max(lev[l].a, row_lo), qhi = std::min(lev[l].b, row_hi);
         if (qlo >= qhi) continue;
         const int N = int(lev[l].b);
-        const GridSpec gs = make_grid(h, double(ordered ? lev[l].a : n), lambda, max_cells);
+        const int ncand = int(std::min<int64_t>(N, cand_cap));
+        const GridSpec gs = make_grid(h, double(ordered ? std::min(lev[l].a, cand_cap) : n), lambda, max_cells);
         GRID_TRY(cudaMemsetAsync(counts, 0, sizeof(int) * size_t(gs.ncell + 1), stream));
         GRID_TRY(cudaMemsetAsync(qcounts, 0, sizeof(int) * size_t(gs.ncell + 1), stream));
         const int sgrid = int(std::min<int64_t>((N + 255) / 256, int64_t(h->num_sms) * 16));
         if (dim3)
-            cell_count_kernel<true><<<sgrid, 256, 0, stream>>>(h->pts, N, gs, int(qlo), int(qhi), sc.cell_of, counts, qcounts);
+            cell_count_kernel<true><<<sgrid, 256, 0, stream>>>(h->pts, N, ncand, gs, int(qlo), int(qhi), sc.cell_of, counts, qcounts);
         else
-            cell_count_kernel<false><<<sgrid, 256, 0, stream>>>(h->pts, N, gs, int(qlo), int(qhi), sc.cell_of, counts, qcounts);
+            cell_count_kernel<false><<<sgrid, 256, 0, stream>>>(h->pts, N, ncand, gs, int(qlo), int(qhi), sc.cell_of, counts, qcounts);
         GRID_TRY(cudaGetLastError());
         scan_cells_kernel<<<2, 1024, 0, stream>>>(counts, starts, cursor, qcounts, qstarts, qcursor, gs.ncell, sc.sumsq);
         GRID_TRY(cudaGetLastError());
@@ -440,7 +446,7 @@ cudaError_t launch_knn_grid(nngp_handle *h, bool ordered, int m, int64_t row_lo,
                 GRID_TRY(cudaMemcpyAsync(&sumsq, sc.sumsq, sizeof(double), cudaMemcpyDeviceToHost, stream));
                 GRID_TRY(cudaStreamSynchronize(stream));
                 const double est = pow(3.0, deff) * sumsq;
-                if (est > double(N) * double(N) / 32.0) return cudaSuccess;  // *used stays 0
+                if (est > double(ncand) * double(ncand) / 16.0) return cudaSuccess;  // *used stays 0
             }
         }
         if (partial && !filled) {
@@ -449,11 +455,12 @@ cudaError_t launch_knn_grid(nngp_handle *h, bool ordered, int m, int64_t row_lo,
             ++h->launches;
             filled = true;
         }
-        scatter_kernel<<<sgrid, 256, 0, stream>>>(h->pts, N, sc.cell_of, int(qlo), int(qhi), cursor, qcursor, sc.sorted,
+        scatter_kernel<<<sgrid, 256, 0, stream>>>(h->pts, N, ncand, sc.cell_of, int(qlo), int(qhi), cursor, qcursor, sc.sorted,
                                                   sc.qlist);
         GRID_TRY(cudaGetLastError());
         const int nq = int(qhi - qlo);
-        qkern<<<(nq + TQ - 1) / TQ, TQ, smem, stream>>>(h->pts, sc.sorted, starts, sc.cell_of, sc.qlist, nq, gs, m, table);
+        qkern<<<(nq + TQ - 1) / TQ, TQ, smem, stream>>>(h->pts, sc.sorted, starts, sc.cell_of, sc.qlist, nq, gs, m,
+                                                        int(std::min<int64_t>(cand_cap, INT32_MAX)), table);
         GRID_TRY(cudaGetLastError());
         h->launches += 2;
     }
@@ -462,7 +469,7 @@ cudaError_t launch_knn_grid(nngp_handle *h, bool ordered, int m, int64_t row_lo,
         GRID_TRY(cudaGetLastError());
         ++h->launches;
     }
-    if (ordered && row_lo < T0 && T0 > 0) GRID_TRY(launch_knn_brute_rows(h, m, T0, table, stream));
+    if (ordered && row_lo < T0 && T0 > 0) GRID_TRY(launch_knn_brute_rows(h, m, 0, T0, cand_cap, table, stream));
     GRID_TRY(cudaStreamSynchronize(stream));  // scratch is freed on return
 #undef GRID_TRY
     *used = 1;

@@ -19,6 +19,7 @@
 // Bound: the FP64 pipe (5 arithmetic + 1 compare instruction per pair in 2-D); candidates are
 // read from HBM/L2 once per 128 queries.
 #include <math.h>
+#include <stdint.h>
 
 #include "nngp_common.cuh"
 
@@ -111,7 +112,8 @@ __device__ __forceinline__ double dist2_sk(double qx, double qy, double qz, cons
 template <bool DIM3, bool ORDERED>
 __global__ void __launch_bounds__(TQ) knn_ordered_kernel(const double4 *__restrict__ pts, int64_t n,
                                                          int m, int ntiles, int tile_offset,
-                                                         int tile_stride, unsigned int *tile_counter,
+                                                         int tile_stride, int first_tile, int64_t cand_cap,
+                                                         unsigned int *tile_counter,
                                                          int32_t *__restrict__ out)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -133,13 +135,14 @@ __global__ void __launch_bounds__(TQ) knn_ordered_kernel(const double4 *__restri
         if (tid == 0) s_tile = (int)atomicAdd(tile_counter, 1u);
         __syncthreads();
         const int64_t rank = int64_t(tile_offset) + int64_t(s_tile) * tile_stride;
-        if (rank >= ntiles) break;
+        if (rank >= ntiles - first_tile) break;  // tiles below first_tile are not wanted
         const int64_t tile = ntiles - 1 - rank;  // heaviest (largest i) first
         const int64_t q0 = tile * TQ;
         const int64_t i = q0 + tid;
         const bool live = i < n;
         const int64_t last_q = (q0 + TQ < n ? q0 + TQ : n) - 1;  // largest live query of the tile
-        const int64_t ncand = ORDERED ? last_q : n;              // candidates 0 .. last_q-1 (or all rows)
+        // candidates 0 .. last_q-1, never beyond cand_cap (or all rows)
+        const int64_t ncand = ORDERED ? (last_q < cand_cap ? last_q : cand_cap) : n;
         const int nct = int((ncand + TC - 1) / TC);
 
         double qx = 0.0, qy = 0.0, qz = 0.0;
@@ -195,7 +198,7 @@ __global__ void __launch_bounds__(TQ) knn_ordered_kernel(const double4 *__restri
                 // diagonal / ragged tile: only predecessors j < i count
                 int lim = 0;
                 if (live) {
-                    const int64_t v = ORDERED ? i - c0 : int64_t(jn);
+                    const int64_t v = ORDERED ? (i < cand_cap ? i : cand_cap) - c0 : int64_t(jn);
                     lim = v < 0 ? 0 : (v > jn ? jn : int(v));
                 }
                 for (int jj = 0; jj < jn; ++jj) {
@@ -230,7 +233,8 @@ inline size_t smem_bytes(int m)
 }  // namespace nngp_knn
 
 static cudaError_t launch_knn(nngp_handle *h, bool ordered, int m, int tile_offset, int tile_stride,
-                              int32_t *table, cudaStream_t stream, int64_t n_rows = -1)
+                              int32_t *table, cudaStream_t stream, int64_t n_rows = -1, int64_t first_row = 0,
+                              int64_t cand_cap = INT64_MAX)
 {
     using namespace nngp_knn;
     const int64_t n = n_rows >= 0 ? n_rows : h->n;  // rows >= n are neither queries nor candidates
@@ -250,10 +254,12 @@ static cudaError_t launch_knn(nngp_handle *h, bool ordered, int m, int tile_offs
     int per_sm = 1;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, TQ, smem) != cudaSuccess || per_sm < 1)
         per_sm = 1;
-    const int my_tiles = (ntiles - tile_offset + tile_stride - 1) / tile_stride;
+    const int first_tile = int(first_row / TQ);
+    const int my_tiles = (ntiles - first_tile - tile_offset + tile_stride - 1) / tile_stride;
     int grid = h->num_sms * per_sm;
     if (grid > my_tiles) grid = my_tiles > 0 ? my_tiles : 1;
-    kern<<<grid, TQ, smem, stream>>>(h->pts, n, m, ntiles, tile_offset, tile_stride, h->d_tile_counter, table);
+    kern<<<grid, TQ, smem, stream>>>(h->pts, n, m, ntiles, tile_offset, tile_stride, first_tile, cand_cap,
+                                     h->d_tile_counter, table);
     ++h->launches;
     return cudaGetLastError();
 }
@@ -263,9 +269,10 @@ cudaError_t launch_knn_ordered(nngp_handle *h, int m, int tile_offset, int tile_
     return launch_knn(h, true, m, tile_offset, tile_stride, h->nbr, stream);
 }
 
-cudaError_t launch_knn_brute_rows(nngp_handle *h, int m, int64_t n_rows, int32_t *d_table, cudaStream_t stream)
+cudaError_t launch_knn_brute_rows(nngp_handle *h, int m, int64_t first_row, int64_t n_rows, int64_t cand_cap,
+                                  int32_t *d_table, cudaStream_t stream)
 {
-    return launch_knn(h, true, m, 0, 1, d_table, stream, n_rows);
+    return launch_knn(h, true, m, 0, 1, d_table, stream, n_rows, first_row, cand_cap);
 }
 
 cudaError_t launch_knn_plain(nngp_handle *h, int k, int32_t *d_table, cudaStream_t stream)

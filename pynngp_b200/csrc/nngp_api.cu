@@ -1,6 +1,7 @@
 // nngp_api.cu -- the C ABI of libnngp_b200.so (include/nngp_b200.h): handle, uploads, dispatch.
 // No CPU fallback exists anywhere in this library: every compute entry point launches a kernel.
 #include <math.h>
+#include <stdint.h>
 #include <stdio.h>
 #include <string.h>
 
@@ -259,11 +260,12 @@ int nngp_build_neighbors(nngp_handle *h, int m, int tile_offset, int tile_stride
     return NNGP_OK;
 }
 
-int nngp_build_neighbors_grid(nngp_handle *h, int m, int64_t row_lo, int64_t row_hi, int algo)
+static int build_neighbors_capped(nngp_handle *h, int m, int64_t row_lo, int64_t row_hi, int64_t cand_cap, int algo)
 {
     if (!h) return fail(nullptr, NNGP_EINVAL, "null handle");
     if (!h->pts) return fail(h, NNGP_ESTATE, "nngp_set_data has not been called");
     if (row_lo < 0 || row_hi < row_lo || row_hi > h->n) return fail(h, NNGP_EINVAL, "need 0 <= row_lo <= row_hi <= n");
+    if (cand_cap < 1) return fail(h, NNGP_EINVAL, "cand_cap must be >= 1");
     if (algo != NNGP_KNN_AUTO && algo != NNGP_KNN_GRID && algo != NNGP_KNN_BRUTE)
         return fail(h, NNGP_EINVAL, "algo must be NNGP_KNN_AUTO, NNGP_KNN_GRID or NNGP_KNN_BRUTE");
     CUDA_TRY(h, cudaSetDevice(h->device));
@@ -271,19 +273,30 @@ int nngp_build_neighbors_grid(nngp_handle *h, int m, int64_t row_lo, int64_t row
     if (rc) return rc;
     int used = 0;
     if (algo != NNGP_KNN_BRUTE) {
-        CUDA_TRY(h, launch_knn_grid(h, true, m, row_lo, row_hi, h->nbr, h->stream, algo == NNGP_KNN_GRID, &used));
+        CUDA_TRY(h, launch_knn_grid(h, true, m, row_lo, row_hi, cand_cap, h->nbr, h->stream, algo == NNGP_KNN_GRID, &used));
         if (!used && algo == NNGP_KNN_GRID) return fail(h, NNGP_EINVAL, "grid search needs finite coordinates");
     }
     if (!used) {
-        // brute force over every row up to row_hi (rows below row_lo come out correct rather than unset)
-        CUDA_TRY(h, launch_knn_brute_rows(h, m, row_hi, h->nbr, h->stream));
-        if (row_hi < h->n)
-            CUDA_TRY(h, launch_fill_i32(h, h->nbr + row_hi * m, (h->n - row_hi) * m, NNGP_ROW_UNSET, h->stream));
+        // brute force over the query tiles covering [row_lo, row_hi); every other row is unset
+        const int64_t t_lo = row_lo / NNGP_KNN_TILE * NNGP_KNN_TILE;
+        CUDA_TRY(h, launch_fill_i32(h, h->nbr, t_lo * m, NNGP_ROW_UNSET, h->stream));
+        CUDA_TRY(h, launch_knn_brute_rows(h, m, t_lo, row_hi, cand_cap, h->nbr, h->stream));
+        CUDA_TRY(h, launch_fill_i32(h, h->nbr + row_hi * m, (h->n - row_hi) * m, NNGP_ROW_UNSET, h->stream));
     }
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     h->knn_used_grid = used;
     h->has_nbr = true;
     return NNGP_OK;
+}
+
+int nngp_build_neighbors_grid(nngp_handle *h, int m, int64_t row_lo, int64_t row_hi, int algo)
+{
+    return build_neighbors_capped(h, m, row_lo, row_hi, INT64_MAX, algo);
+}
+
+int nngp_build_neighbors_capped(nngp_handle *h, int m, int64_t row_lo, int64_t row_hi, int64_t cand_cap, int algo)
+{
+    return build_neighbors_capped(h, m, row_lo, row_hi, cand_cap, algo);
 }
 
 int nngp_set_knn_tuning(nngp_handle *h, double lambda_scale, int64_t brute_rows)
@@ -322,6 +335,18 @@ int nngp_get_neighbors(nngp_handle *h, int32_t *out)
     return NNGP_OK;
 }
 
+int nngp_get_neighbor_rows(nngp_handle *h, int64_t i0, int64_t i1, int32_t *out)
+{
+    if (!h) return fail(nullptr, NNGP_EINVAL, "null handle");
+    if (!h->has_nbr) return fail(h, NNGP_ESTATE, "no neighbour table");
+    if (!out || i0 < 0 || i1 < i0 || i1 > h->n) return fail(h, NNGP_EINVAL, "need out != NULL and 0 <= i0 <= i1 <= n");
+    if (i1 == i0) return NNGP_OK;
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    CUDA_TRY(h, cudaMemcpyAsync(out, h->nbr + i0 * h->m, sizeof(int32_t) * size_t(i1 - i0) * h->m, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return NNGP_OK;
+}
+
 int nngp_knn_plain(nngp_handle *h, int k, int32_t *out)
 {
     if (!h) return fail(nullptr, NNGP_EINVAL, "null handle");
@@ -331,7 +356,7 @@ int nngp_knn_plain(nngp_handle *h, int k, int32_t *out)
     int32_t *d_tab = nullptr;
     CUDA_TRY(h, cudaMalloc(&d_tab, sizeof(int32_t) * (size_t)h->n * k));
     int used = 0;
-    cudaError_t e = launch_knn_grid(h, false, k, 0, h->n, d_tab, h->stream, 0, &used);
+    cudaError_t e = launch_knn_grid(h, false, k, 0, h->n, INT64_MAX, d_tab, h->stream, 0, &used);
     if (e == cudaSuccess && !used) e = launch_knn_plain(h, k, d_tab, h->stream);
     if (e == cudaSuccess) e = cudaMemcpyAsync(out, d_tab, sizeof(int32_t) * (size_t)h->n * k, cudaMemcpyDeviceToHost, h->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);

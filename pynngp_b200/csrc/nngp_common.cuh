@@ -74,9 +74,12 @@ cudaError_t launch_knn_ordered(nngp_handle *h, int m, int tile_offset, int tile_
                                cudaStream_t stream);
 cudaError_t launch_knn_plain(nngp_handle *h, int k, int32_t *d_table, cudaStream_t stream);
 cudaError_t launch_fill_i32(nngp_handle *h, int32_t *p, int64_t count, int32_t v, cudaStream_t stream);
-// brute force restricted to rows [0, n_rows) of the ordering
-cudaError_t launch_knn_brute_rows(nngp_handle *h, int m, int64_t n_rows, int32_t *d_table, cudaStream_t stream);
-// grid search (knn_grid.cu) for rows [row_lo, row_hi); *used = 0 when the data does not suit a grid
-cudaError_t launch_knn_grid(nngp_handle *h, bool ordered, int m, int64_t row_lo, int64_t row_hi, int32_t *table,
-                            cudaStream_t stream, int force, int *used);
+// brute force restricted to the query tiles covering rows [first_row, n_rows) of the ordering;
+// candidates of row i are j < min(i, cand_cap)
+cudaError_t launch_knn_brute_rows(nngp_handle *h, int m, int64_t first_row, int64_t n_rows, int64_t cand_cap,
+                                  int32_t *d_table, cudaStream_t stream);
+// grid search (knn_grid.cu) for rows [row_lo, row_hi), candidates j < min(i, cand_cap); *used = 0 when
+// the data does not suit a grid
+cudaError_t launch_knn_grid(nngp_handle *h, bool ordered, int m, int64_t row_lo, int64_t row_hi, int64_t cand_cap,
+                            int32_t *table, cudaStream_t stream, int force, int *used);
 cudaError_t launch_fma_peak(nngp_handle *h, int dtype, int iters, double *instr_per_s);

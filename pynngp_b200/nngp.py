@@ -135,6 +135,8 @@ class NNGP(object):
 
         eng = self._engine
         t0 = time.perf_counter()
+        if isinstance(neighbors, (str, bytes)) or hasattr(neighbors, "__fspath__"):
+            neighbors = np.load(neighbors)  # a table written by save_neighbors()
         if neighbors is not None:
             eng.set_neighbors(neighbors)
         elif self._world == 1:
@@ -284,6 +286,85 @@ class NNGP(object):
         slog, squad = self.loglik_terms(sigma2, phi, tau2)
         ncol = self._y2d.shape[1]
         return -0.5 * (slog + squad) - 0.5 * len(self._coords) * ncol * LOG_2PI
+
+    # ---- either side of the path: table I/O, kriging at new sites, a sweep driver ---------------------
+    def save_neighbors(self, path):
+        """Writes the (n, m) int32 neighbour table as .npy; pass the path as ``neighbors=`` to a later
+        constructor on the same sites to skip stage 1."""
+        np.save(path, self._table)
+
+    def predict(self, t_new, sigma2=None, phi=None, tau2=None, m=None):
+        """Kriging at new sites from their m nearest REFERENCE sites (NNGP prediction): returns
+        (mean, var) with mean = b^T y_N and var = C(0) + tau2 - c^T C_N^-1 c, the variance of a new noisy
+        observation (subtract tau2 for the latent field).  Runs the hot path's own kernels: the new sites
+        are appended after the n reference sites, stage 1 is restricted to candidates j < n, and the
+        emitting variant of the fused kernel returns b and F for the appended rows."""
+        tn = np.ascontiguousarray(t_new, dtype=np.float64)
+        if tn.ndim == 1:
+            tn = tn[:, None] if self._coords.shape[1] == 1 else tn[None, :]
+        if tn.shape[1] != self._coords.shape[1]:
+            raise ValueError("t_new must have the reference sites' dimension")
+        if not np.isfinite(tn).all():
+            raise ValueError("coordinates must be finite")
+        n, q = len(self._coords), len(tn)
+        m = self.m if m is None else int(m)
+        prm = self._params(sigma2, phi, tau2)
+        ncol = self._y2d.shape[1]
+        mean = np.zeros((q, ncol))
+        var = np.zeros((q, ncol))
+        if q == 0:
+            return mean.reshape((0,) + np.shape(self.y)[1:]), var.reshape((0,) + np.shape(self.y)[1:])
+        eng = _lib.Engine(device=self._engine.device, dtype=self._engine.dtype)
+        coords = np.concatenate([self._coords, tn])
+        B = F = tab = None
+        for c in range(ncol):
+            if B is None or self._eps2 is not None:  # weights depend on the column only through eps
+                eps2 = None if self._eps2 is None else np.concatenate([self._eps2[:, c], np.zeros(q)])
+                eng.set_data(coords, np.concatenate([self._y2d[:, c], np.zeros(q)]), eps2)
+                if tab is None:
+                    eng.build_neighbors_capped(m, n, n + q, n, self._knn)
+                    tab = eng.get_neighbor_rows(n, n + q)
+                    full = eng.get_neighbors() if self._eps2 is not None else None
+                else:
+                    eng.set_neighbors(full)
+                B, F = eng.factors(self._kernel.kernel_id, prm, n, n + q)
+            yn = np.where(tab >= 0, self._y2d[np.maximum(tab, 0), c], 0.0)
+            mean[:, c] = (B * yn).sum(axis=1)
+            var[:, c] = F
+        eng.close()
+        shape = (q,) + np.shape(self.y)[1:]
+        return mean.reshape(shape), var.reshape(shape)
+
+    def metropolis(self, n_steps, init=None, step=0.05, seed=0, log_prior=None):
+        """Random-walk Metropolis over log(sigma2, phi, tau2) with the NNGP likelihood as target
+        (neighbours fixed, one fused-kernel evaluation per step: BASELINE.json configs[4]).  Returns
+        (chain (n_steps, 3), loglik (n_steps,), acceptance rate).  `log_prior(theta)` defaults to flat in
+        log-parameters.  The same random stream on every rank keeps sharded runs in lock step."""
+        rng = np.random.default_rng(seed)
+        theta = np.array(self._kernel.params(None, None, None)[:3] if init is None else init, dtype=np.float64)
+        step = np.broadcast_to(np.asarray(step, dtype=np.float64), (3,))
+        lp = (lambda th: 0.0) if log_prior is None else log_prior
+
+        def target(th):
+            st = self.loglik_batch(np.array([[th[0], th[1], th[2], 0.0]]))[0]
+            if st[2] > 0 or not np.isfinite(st[:2]).all():
+                return -np.inf
+            ncol = self._y2d.shape[1]
+            return -0.5 * (st[0] + st[1]) - 0.5 * len(self._coords) * ncol * LOG_2PI
+
+        cur = target(theta)
+        chain = np.empty((n_steps, 3))
+        trace = np.empty(n_steps)
+        acc = 0
+        for k in range(n_steps):
+            prop = theta * np.exp(step * rng.standard_normal(3))
+            val = target(prop)
+            # symmetric in log-parameters: the Jacobian of the log transform enters through log_prior
+            if np.log(rng.random()) < (val + lp(prop)) - (cur + lp(theta)):
+                theta, cur = prop, val
+                acc += 1
+            chain[k], trace[k] = theta, cur
+        return chain, trace, acc / max(n_steps, 1)
 
     def oneSample(self):
         # nngp.py:98-101 calls update_wt / update_ws / update_y_unobserved, none of which exist upstream

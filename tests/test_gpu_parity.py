@@ -380,6 +380,96 @@ def test_class_cfg1_end_to_end():
         obj.oneSample()
 
 
+# ---- either side of the path: prediction, table I/O, sweep driver -----------------
+def numpy_kriging(s, y, tn, m, kid, sigma2, phi, tau2, eps2=None):
+    """Exact restatement: m nearest reference sites in (d2, j) order, dense solve per new site."""
+    mean, var, tabs = [], [], []
+    for t in tn:
+        d2 = orc.np_dist2(t, s)
+        nb = np.lexsort((np.arange(len(s)), d2))[:m]
+        dn = np.sqrt(((s[nb][:, None, :] - s[nb][None, :, :]) ** 2).sum(-1))
+        CN = sigma2 * orc.np_corr(kid, phi * dn)
+        CN[np.diag_indices(len(nb))] = sigma2 + tau2 + (0.0 if eps2 is None else eps2[nb])
+        c = sigma2 * orc.np_corr(kid, phi * np.sqrt(((s[nb] - t) ** 2).sum(-1)))
+        b = np.linalg.solve(CN, c)
+        mean.append(b @ y[nb])
+        var.append(sigma2 + tau2 - c @ b)
+        tabs.append(nb)
+    return np.array(mean), np.array(var), np.array(tabs)
+
+
+@pytest.mark.parametrize("n,D,m,kernel", [(4000, 2, 15, "matern32"), (3000, 3, 30, "exponential"), (2500, 1, 6, "matern52"),
+                                          (20000, 2, 10, "exponential")])
+def test_predict_matches_numpy_kriging(n, D, m, kernel):
+    import pyNNGP
+    from pynngp_b200 import Exponential, Matern
+
+    s, y = synthetic(n, D, 40 + m)
+    rng = np.random.default_rng(n)
+    tn = rng.random((257, D)) * 1.2 - 0.1  # some sites outside the reference bounding box
+    def mk(tau2):
+        return {"exponential": Exponential(1.3, 5.0, tau2), "matern32": Matern(1.5, 1.3, 5.0, tau2),
+                "matern52": Matern(2.5, 1.3, 5.0, tau2)}[kernel]
+
+    spec = mk(0.07)
+    obj = pyNNGP.NNGP(s, y, 0.0, "S=T", m, spec)
+    mean, var = obj.predict(tn)
+    mean0, var0, tab0 = numpy_kriging(s, y, tn, m, KIDS[kernel], 1.3, 5.0, 0.07)
+    np.testing.assert_allclose(mean, mean0, rtol=1e-9, atol=1e-10)
+    np.testing.assert_allclose(var, var0, rtol=1e-9)
+    # the neighbour sets themselves, bit-exact, through the C ABI (grid and brute force)
+    for algo in ("grid", "brute"):
+        e = engine(np.concatenate([s, tn]), np.zeros(n + len(tn)))
+        e.set_knn_tuning(1.0, 256)
+        e.build_neighbors_capped(m, n, n + len(tn), n, algo)
+        assert np.array_equal(e.get_neighbor_rows(n, n + len(tn)), tab0)
+    if kernel == "exponential":
+        # well-conditioned family: a site that coincides with a reference site reproduces it as the
+        # nugget vanishes
+        mu, v = pyNNGP.NNGP(s, y, 0.0, "S=T", m, mk(1e-7)).predict(s[100:103])
+        np.testing.assert_allclose(mu, y[100:103], rtol=0, atol=1e-3)
+        assert (v > 0).all() and (v < 1e-5).all()
+
+
+def test_predict_two_columns_and_eps():
+    import pyNNGP
+
+    s, y = synthetic(1500, 2, 9)
+    y2 = np.stack([y, -2 * y], axis=1)
+    eps = np.stack([np.full(1500, 0.1), np.linspace(0.0, 0.3, 1500)], axis=1)
+    from pynngp_b200 import Exponential
+
+    obj = pyNNGP.NNGP(s, y2, eps, "S=T", 8, Exponential(1.0, 6.0, 0.1))
+    tn = np.random.default_rng(0).random((40, 2))
+    mean, var = obj.predict(tn)
+    assert mean.shape == (40, 2) and var.shape == (40, 2)
+    p = obj._params()
+    for c in range(2):
+        m0, v0, _ = numpy_kriging(s, y2[:, c], tn, 8, 0, p[0], p[1], p[2], eps2=eps[:, c] ** 2)
+        np.testing.assert_allclose(mean[:, c], m0, rtol=1e-9, atol=1e-10)
+        np.testing.assert_allclose(var[:, c], v0, rtol=1e-9)
+
+
+def test_save_neighbors_roundtrip_and_metropolis(tmp_path):
+    import pyNNGP
+    from pynngp_b200 import Matern
+
+    s, y = synthetic(6000, 2, 14)
+    spec = Matern(1.5, 1.0, 6.0, 0.1)
+    a = pyNNGP.NNGP(s, y, 0.0, "S=T", 10, spec)
+    path = str(tmp_path / "nbr.npy")
+    a.save_neighbors(path)
+    b = pyNNGP.NNGP(s, y, 0.0, "S=T", 10, spec, neighbors=path)
+    assert np.array_equal(a._table, b._table) and a.loglik() == b.loglik()
+    chain, trace, rate = b.metropolis(60, step=0.08, seed=3)
+    assert chain.shape == (60, 3) and np.isfinite(chain).all() and (chain > 0).all()
+    assert 0.0 < rate < 1.0
+    assert trace[-1] == b.loglik(*chain[-1])                      # the trace is the target at the chain's states
+    assert trace.max() >= a.loglik() - 1e-9 or rate > 0             # moved towards higher density or stayed
+    chain2, trace2, _ = b.metropolis(60, step=0.08, seed=3)
+    assert np.array_equal(chain, chain2) and np.array_equal(trace, trace2)  # deterministic given the seed
+
+
 # ---- full-size properties (no oracle at this size) -----------------------------------------------
 def test_cfg3_full_size_properties():
     c = CONFIGS["cfg3"]
