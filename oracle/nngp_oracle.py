@@ -132,6 +132,29 @@ class NumpyNNGP:
         return slog, squad
 
 
+def np_krige(s, y, tn, m, kernel_id, sigma2, phi, tau2, eps2=None):
+    """Kriging at new sites `tn` from the m nearest reference sites, (d2, j) order -- the step after the
+    path (the reference names it only through oneSample's undefined update_y_unobserved,
+    nngp.py:98-101).  mean = c^T C_N^-1 y_N, var = sigma2 + tau2 - c^T C_N^-1 c, C_N with the same
+    diagonal as _CNs (nngp.py:78-82 restated above).  Returns (mean, var, neighbour table)."""
+    s = np.asarray(s, dtype=np.float64)
+    if s.ndim == 1:
+        s = s[:, None]
+    tn = np.asarray(tn, dtype=np.float64).reshape(-1, s.shape[1])
+    mean, var, tabs = [], [], []
+    for t in tn:
+        nb = np.lexsort((np.arange(len(s)), np_dist2(t, s)))[:m]
+        dn = np.sqrt(((s[nb][:, None, :] - s[nb][None, :, :]) ** 2).sum(-1))
+        CN = sigma2 * np_corr(kernel_id, phi * dn)
+        CN[np.diag_indices(len(nb))] = sigma2 + tau2 + (0.0 if eps2 is None else np.asarray(eps2)[nb])
+        c = sigma2 * np_corr(kernel_id, phi * np.sqrt(((s[nb] - t) ** 2).sum(-1)))
+        b = np.linalg.solve(CN, c)
+        mean.append(b @ np.asarray(y)[nb])
+        var.append(sigma2 + tau2 - c @ b)
+        tabs.append(nb)
+    return np.array(mean), np.array(var), np.array(tabs)
+
+
 def loglik_from_terms(slog, squad, n):
     """log N(y; 0, C_nngp) from the north_star reduction."""
     return -0.5 * (slog + squad) - 0.5 * n * np.log(2.0 * np.pi)

@@ -336,7 +336,9 @@ template <> struct Pair2<float> { using type = float2; };
 // ELIM = 0: pivot-column entries travel by width-G warp shuffles.  ELIM = 1: the lanes publish the
 // column in shared memory once per pivot and read it back as broadcast 2-element loads -- a quarter
 // of the instructions the 64-bit shuffles (two SHFL plus their register moves each) cost.
-template <typename T, int G, int R, int KERN, bool DIM3, int MINB, int BUILD, int ELIM>
+// EMIT: the variant that also writes per-location outputs (accessors, factors(), prediction); compiled
+// separately so the metric's kernel carries none of its code or registers.
+template <typename T, int G, int R, int KERN, bool DIM3, int MINB, int BUILD, int ELIM, bool EMIT>
 __global__ void __launch_bounds__(kThreads, MINB) fused_loglik_kernel(const EvalArgs a)
 {
     constexpr int P = G * R;   // rows of the augmented matrix
@@ -352,7 +354,7 @@ __global__ void __launch_bounds__(kThreads, MINB) fused_loglik_kernel(const Eval
 
     T *exp_tab = reinterpret_cast<T *>(smem_raw);  // sigma2 * 2^(j/64) (fp64 path only)
     uint2 *pair_lut = reinterpret_cast<uint2 *>(smem_raw + exp_tab_bytes<T, G, BUILD>());
-    unsigned char *wbase = smem_raw + block_smem<T, G, R, BUILD>() + size_t(warp) * WS::total(a.emit != 0);
+    unsigned char *wbase = smem_raw + block_smem<T, G, R, BUILD>() + size_t(warp) * WS::total(EMIT);
     unsigned char *recbuf = wbase + g * WS::rec_stride;  // this location's records (16-byte aligned)
     double *e2buf = reinterpret_cast<double *>(wbase + WS::rec);
     int *idxbuf = reinterpret_cast<int *>(wbase + WS::rec + WS::e2) + lane;          // [s * 32]
@@ -373,7 +375,10 @@ __global__ void __launch_bounds__(kThreads, MINB) fused_loglik_kernel(const Eval
     constexpr int TB = exp_tab_bits<G, BUILD>();
     if constexpr (sizeof(T) == 8)
         for (int k = threadIdx.x; k < (1 << TB); k += kThreads) exp_tab[k] = T(prm[0] * exp2(double(k) / (1 << TB)));
-    accbuf[0] = 0.0; accbuf[32] = 0.0; accbuf[64] = 0.0;  // sum log F, sum r^2/F, n_bad: rarely touched,
+    // sum log F is carried as log(prod of mantissas) + ln2 * (sum of exponents): one multiply and a few
+    // integer operations per location instead of a log() the whole warp would issue for one lane in G
+    int nbad = 0;
+    accbuf[0] = 1.0; accbuf[32] = 0.0; accbuf[64] = 0.0;  // mantissa product, sum r^2/F, exponent sum: rarely touched,
                                                             // kept out of the register file
     // The launch's pair list: rows in play are the m neighbour rows and the location's own row P-1
     // (rows m .. P-2 are identity padding: their entries stay at the zero the tile is filled with).
@@ -586,7 +591,7 @@ __global__ void __launch_bounds__(kThreads, MINB) fused_loglik_kernel(const Eval
         }
         __syncwarp();  // tile and stage[] are rewritten by the next iteration
 
-        if (a.emit && live) {
+        if (EMIT && live) {
             // per-location covariance blocks (the _CNs/_Ccross/_Cs accessors; parity output)
             const int64_t o = i - a.lo;
 #pragma unroll
@@ -696,15 +701,28 @@ __global__ void __launch_bounds__(kThreads, MINB) fused_loglik_kernel(const Eval
         }
 
         if (live && q == 0) {
+            const double Fd = double(Flast);
+            bad |= !(Fd < INFINITY);
             if (bad) {
-                accbuf[64] += 1.0;
+                ++nbad;
             } else {
-                accbuf[0] += log(double(Flast));
-                accbuf[32] += double(rlast) * double(rlast) / double(Flast);
+                const int hi = __double2hiint(Fd);
+                if (hi >= 0x00100000) {
+                    // F = mant * 2^e, mant in [1, 2); the running product stays in [1, 2) as well
+                    const double mant = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(Fd));
+                    const double pr = accbuf[0] * mant;
+                    const int ph = __double2hiint(pr);
+                    const int carry = (ph >> 20) - 1023;  // 0 or 1
+                    accbuf[0] = __hiloint2double(ph - (carry << 20), __double2loint(pr));
+                    accbuf[64] += double((hi >> 20) - 1023 + carry);
+                } else {
+                    accbuf[64] += log2(Fd);  // subnormal F: the exponent field is not usable
+                }
+                accbuf[32] = fma(double(rlast) * double(rlast), fast_rcp(Fd), accbuf[32]);
             }
         }
 
-        if (a.emit) {
+        if constexpr (EMIT) {
             // b_i = L_N^{-T} ell, ell = last row of the unit-lower factor.  One location at a time:
             // its G lanes dump their rows to shared memory and lane 0 back-substitutes (parity /
             // prediction output, not the metric's path).
@@ -738,9 +756,9 @@ __global__ void __launch_bounds__(kThreads, MINB) fused_loglik_kernel(const Eval
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");  // drain copies issued for groups past the end
 
-    double acc_log = accbuf[0], acc_quad = accbuf[32];
+    double acc_log = fma(accbuf[64], 0.6931471805599453094, log(accbuf[0])), acc_quad = accbuf[32];
     // ---- reduction: warp shuffle tree -> block -> per-block partial -> last block sums ------
-    double bad_d = accbuf[64];
+    double bad_d = double(nbad);
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) {
         acc_log += __shfl_xor_sync(0xffffffffu, acc_log, off);
@@ -796,7 +814,8 @@ __global__ void __launch_bounds__(kThreads, MINB) fused_loglik_kernel(const Eval
 template <typename T, int G, int R, int KERN, bool DIM3, int MINB, int BUILD, int ELIM>
 cudaError_t launch_one(const EvalArgs &a, int K, int grid_x, cudaStream_t stream)
 {
-    auto kern = fused_loglik_kernel<T, G, R, KERN, DIM3, MINB, BUILD, ELIM>;
+    auto kern = a.emit ? fused_loglik_kernel<T, G, R, KERN, DIM3, MINB, BUILD, ELIM, true>
+                       : fused_loglik_kernel<T, G, R, KERN, DIM3, MINB, BUILD, ELIM, false>;
     const size_t smem = smem_bytes<T, G, R, DIM3, BUILD>(a.emit != 0);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
@@ -810,7 +829,7 @@ cudaError_t launch_one(const EvalArgs &a, int K, int grid_x, cudaStream_t stream
 template <typename T, int G, int R, int KERN, bool DIM3, int MINB, int BUILD, int ELIM>
 int blocks_per_sm()
 {
-    auto kern = fused_loglik_kernel<T, G, R, KERN, DIM3, MINB, BUILD, ELIM>;
+    auto kern = fused_loglik_kernel<T, G, R, KERN, DIM3, MINB, BUILD, ELIM, false>;
     int nb = 0;
     const size_t smem = smem_bytes<T, G, R, DIM3, BUILD>(false);
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -151,3 +151,22 @@ def test_non_spd_is_counted_not_nan():
 
 def test_golden_files_present(golden_dir):
     assert len(glob.glob(os.path.join(golden_dir, "ns_*.npz"))) >= 7
+
+
+def test_krige_known_answers():
+    """m = n: nearest-neighbour kriging is exact GP conditioning -- mean and variance equal the dense
+    formulas; a new site far from every reference site returns the prior (0, sigma2 + tau2)."""
+    rng = np.random.default_rng(3)
+    s = rng.random((40, 2))
+    y = rng.standard_normal(40)
+    tn = rng.random((5, 2))
+    for kid in (0, 1, 2):
+        mean, var, tab = orc.np_krige(s, y, tn, 40, kid, 1.2, 4.0, 0.05)
+        d = np.sqrt(((s[:, None, :] - s[None, :, :]) ** 2).sum(-1))
+        C = 1.2 * orc.np_corr(kid, 4.0 * d) + 0.05 * np.eye(40)
+        c = 1.2 * orc.np_corr(kid, 4.0 * np.sqrt(((s[None, :, :] - tn[:, None, :]) ** 2).sum(-1)))
+        np.testing.assert_allclose(mean, c @ np.linalg.solve(C, y), rtol=1e-9, atol=1e-12)
+        np.testing.assert_allclose(var, 1.25 - np.einsum("qi,qi->q", c, np.linalg.solve(C, c.T).T), rtol=1e-9)
+        assert sorted(tab[0].tolist()) == list(range(40))
+    mean, var, _ = orc.np_krige(s, y, np.array([[500.0, 500.0]]), 6, 0, 1.2, 4.0, 0.05)
+    assert abs(mean[0]) < 1e-200 and var[0] == 1.25
