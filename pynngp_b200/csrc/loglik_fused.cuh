@@ -309,7 +309,7 @@ struct WarpSmem {
 
 // block-shared part: exp table + the launch's pair list (one packed word per pair)
 template <int G, int BUILD>
-__host__ __device__ constexpr int exp_tab_bits() { return BUILD == 0 ? 11 : (G == 16 ? 6 : 8); }
+__host__ __device__ constexpr int exp_tab_bits() { return BUILD != 1 ? 11 : (G == 16 ? 6 : 8); }
 // pairs evaluated in lock step by one lane: 8 in the rolled (8, 4) build, whose loop is bound by the
 // latency of its dependent shared-memory reads (pair list -> coordinates -> exp table)
 template <int G, int BUILD>
@@ -561,7 +561,8 @@ __global__ void __launch_bounds__(kThreads, MINB) fused_loglik_kernel(const Eval
             // independent chains, whichever rows/columns they belong to (batching by column alone runs
             // out of parallelism on the late columns, which only the last row block needs) -- and the
             // results go straight to the row registers.
-            constexpr int CB = 4;
+            // BUILD selects the unrolled build's batch width: 0 -> 4, 2 -> 6, 3 -> 9, 4 -> 12 pairs in lock step
+            constexpr int CB = BUILD == 0 ? 4 : BUILD == 2 ? 6 : BUILD == 3 ? 9 : 12;
             constexpr int NP = G * R * (R + 1) / 2 - R;  // sum over s of (s*G + G - 1)
 #pragma unroll
             for (int t0 = 0; t0 < NP; t0 += CB) {
@@ -839,7 +840,8 @@ int blocks_per_sm()
 
 // ---- shape table: (G lanes per location, R rows per lane) -> P = G*R >= m + 1 rows --------------------
 //   m <=  7 : (4, 2) unrolled row-owner build
-//   m <= 15 : (4, 4) unrolled row-owner build (fp64: 168 registers, 12 warps/SM)
+//   m <= 15 : (4, 4) unrolled row-owner build, fp64: 6-pair batches, 255 registers, 8 warps/SM (in-thread
+//             parallelism hides the FP64 latency better than a third block of warps did: 0.433 vs 0.452 ms)
 //   m <= 31 : (8, 4) rolled pair-list build
 //   m == 32 : (16, 3) rolled pair-list build
 // MINB = resident blocks per SM the kernel is compiled for (the register cap).
@@ -868,21 +870,16 @@ template <typename T, bool DIM3, typename F>
 auto dispatch_shape(int m, const F &f)
 {
     constexpr bool F64 = sizeof(T) == 8;
-#ifdef NNGP_TUNE  // development knobs: NNGP_TUNE_ELIM = 0 selects the shuffle elimination
-    if (const char *e = getenv("NNGP_TUNE_ELIM"); e && atoi(e) == 0) {
-        if (m <= 7) return f.template run<4, 2, DIM3, 4, 0, 0>();
-        if (m <= 15) return f.template run<4, 4, DIM3, (F64 ? 3 : 4), 0, 0>();
-        if (m <= 31) return f.template run<8, 4, DIM3, (F64 ? 2 : 4), 1, 0>();
-        return f.template run<16, 3, DIM3, (F64 ? 2 : 4), 1, 0>();
-    }
+#ifdef NNGP_TUNE  // development knobs for the m <= 15, D < 3 shape (results: DESIGN.md 5.3)
     if (const char *e = getenv("NNGP_TUNE_SHAPE"); e && m > 7 && m <= 15 && !DIM3) {
-        if (!strcmp(e, "4x4r")) return f.template run<4, 4, DIM3, 2, 1>();
-        if (!strcmp(e, "4x4u2")) return f.template run<4, 4, DIM3, 2, 0>();
-        if (!strcmp(e, "8x2u")) return f.template run<8, 2, DIM3, 4, 0>();
+        if (!strcmp(e, "shfl")) return f.template run<4, 4, DIM3, 2, 2, 0>();   // shuffle elimination
+        if (!strcmp(e, "4x4r")) return f.template run<4, 4, DIM3, 2, 1>();      // rolled pair-list build
+        if (!strcmp(e, "m3cb4")) return f.template run<4, 4, DIM3, 3, 0>();     // 12 warps/SM, 4-pair batches
+        if (!strcmp(e, "m2cb12")) return f.template run<4, 4, DIM3, 2, 4>();    // 12-pair batches
     }
 #endif
     if (m <= 7) return f.template run<4, 2, DIM3, 4, 0>();
-    if (m <= 15) return f.template run<4, 4, DIM3, (F64 ? 3 : 4), 0>();
+    if (m <= 15) return f.template run<4, 4, DIM3, (F64 ? 2 : 4), (F64 ? 2 : 0)>();
     if (m <= 31) return f.template run<8, 4, DIM3, (F64 ? 2 : 4), 1>();
     return f.template run<16, 3, DIM3, (F64 ? 2 : 4), 1>();
 }
