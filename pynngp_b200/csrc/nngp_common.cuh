@@ -30,7 +30,7 @@ struct nngp_handle {
     bool bb_finite = false;                              // every coordinate finite
     double knn_lambda_scale = 1.0;                       // grid k-NN: cell occupancy multiplier
     int knn_used_grid = 0;                               // last stage-1 build went through the grid
-    int64_t knn_brute_rows = 8192;                       // grid k-NN: rows below this use brute force
+    int64_t knn_brute_rows = 4096;                       // grid k-NN: rows below this use brute force
 
     double4 *pts = nullptr;
     double *eps2 = nullptr;
