@@ -193,10 +193,15 @@ def run_ours(args, cfg):
     stream = torch.cuda.Stream()  # a real stream: the C ABI treats NULL as 'the handle's own stream'
     torch.cuda.set_stream(stream)
 
+    fused_exchange = world > 1 and model._peer_ok and not args.nccl_allreduce
+
     def step_device():
-        eng.loglik_device(kid, d_prm.data_ptr(), 1, d_out.data_ptr(), stream.cuda_stream)
-        if world > 1:
-            dist.all_reduce(d_out)
+        if fused_exchange:  # kernel + sum over ranks through NVLink peer memory in one launch
+            eng.loglik_device_allreduce(kid, d_prm.data_ptr(), 1, d_out.data_ptr(), stream.cuda_stream)
+        else:
+            eng.loglik_device(kid, d_prm.data_ptr(), 1, d_out.data_ptr(), stream.cuda_stream)
+            if world > 1:
+                dist.all_reduce(d_out)
 
     def barrier():
         if world > 1:
@@ -325,6 +330,9 @@ def run_ours(args, cfg):
     # parity spot check on the very numbers being timed (cheap: the sample's rows)
     ms_per_step = total_ms / args.steps
     cfgd = workload_config(cfg, world)
+    cfgd["exchange"] = ("none (1 GPU)" if world == 1 else
+                        "fused into the kernel: P2P stores over NVLink peer memory (CUDA IPC), no NCCL call" if fused_exchange
+                        else "NCCL all_reduce of 3 doubles after the kernel")
     cfgd.update({"setup_s": setup_s, "knn_build_s": knn_s, "knn_algo": "grid" if eng.knn_used_grid() else "brute",
                  "cold_e2e": {"ms": cold_s * 1e3, "knn_ms": cold_knn * 1e3, "h2d_bytes": int(cfg["n"]) * 32, "d2h_bytes": 24,
                               "what": "pyNNGP.NNGP(t, y, eps, 'S=T', m, cov) from host arrays (upload + stage 1) + one "
@@ -354,6 +362,7 @@ def main():
     ap.add_argument("--config", default="cfg3", choices=sorted(CONFIGS))
     ap.add_argument("--dtype", default="float64", choices=["float64", "float32"])
     ap.add_argument("--cpu-sample", type=int, default=16384)
+    ap.add_argument("--nccl-allreduce", action="store_true", help="multi-GPU: sum the statistics with NCCL instead of the fused peer-memory exchange")
     args = ap.parse_args()
     cfg = CONFIGS[args.config]
     if args.impl == "reference":

@@ -118,6 +118,21 @@ int nngp_loglik(nngp_handle *h, int kernel_id, const double *params, int K, doub
 int nngp_loglik_device(nngp_handle *h, int kernel_id, const double *d_params, int K,
                        double *d_out, void *stream);
 
+/* Multi-GPU evaluation with the sum over ranks fused into the kernel (one process per GPU of ONE node).
+ * Each rank calls nngp_peer_export (allocates its exchange buffer for up to K_cap parameter vectors and
+ * returns its CUDA IPC handle, NNGP_IPC_HANDLE_BYTES bytes), the caller gathers the `world` handles in
+ * rank order (any transport; pynngp_b200 uses torch.distributed), and every rank calls nngp_peer_connect.
+ * nngp_loglik_device_allreduce then behaves like nngp_loglik_device except that d_out receives the sum over
+ * ALL ranks, bitwise identical on every rank: the last block of each rank stores its K x 3 partials into
+ * every peer's buffer over NVLink (P2P stores), flags them, waits for all ranks' flags and sums in rank
+ * order -- no second launch, no NCCL call.  Every rank must issue the same sequence of these calls.  If a
+ * peer does not arrive within ~2 s the statistics come back as NaN. */
+#define NNGP_IPC_HANDLE_BYTES 64
+int nngp_peer_export(nngp_handle *h, int K_cap, unsigned char *handle_out);
+int nngp_peer_connect(nngp_handle *h, int rank, int world, const unsigned char *handles);
+int nngp_loglik_device_allreduce(nngp_handle *h, int kernel_id, const double *d_params, int K,
+                                 double *d_out, void *stream);
+
 /* Per-location factors for rows [i0, i1) (any rows, not only the shard): B (i1-i0) x m fp64
  * (b_i = C_N(i)^-1 c_i, zero padded; _Bsi nngp.py:73-76), F (i1-i0) (_Fsi nngp.py:88-90).
  * Either output may be NULL. */

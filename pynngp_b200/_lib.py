@@ -18,6 +18,7 @@ NPARAM, NSTAT = 4, 3
 MAX_M, MAX_D = 32, 3
 KNN_TILE = 128
 ROW_UNSET = -2
+IPC_HANDLE_BYTES = 64
 
 _c_double_p = ctypes.POINTER(ctypes.c_double)
 _c_int32_p = ctypes.POINTER(ctypes.c_int32)
@@ -44,6 +45,9 @@ SIGNATURES = {
     "nngp_neighbors_device_ptr": (ctypes.c_void_p, [_handle_p]),
     "nngp_loglik": (ctypes.c_int, [_handle_p, ctypes.c_int, _c_double_p, ctypes.c_int, _c_double_p]),
     "nngp_loglik_device": (ctypes.c_int, [_handle_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]),
+    "nngp_peer_export": (ctypes.c_int, [_handle_p, ctypes.c_int, ctypes.c_char_p]),
+    "nngp_peer_connect": (ctypes.c_int, [_handle_p, ctypes.c_int, ctypes.c_int, ctypes.c_char_p]),
+    "nngp_loglik_device_allreduce": (ctypes.c_int, [_handle_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]),
     "nngp_factors": (ctypes.c_int, [_handle_p, ctypes.c_int, _c_double_p, ctypes.c_int64, ctypes.c_int64, _c_double_p, _c_double_p]),
     "nngp_cov_blocks": (ctypes.c_int, [_handle_p, ctypes.c_int, _c_double_p, ctypes.c_int64, ctypes.c_int64, _c_double_p, _c_double_p, _c_double_p]),
     "nngp_launch_count": (ctypes.c_int64, [_handle_p]),
@@ -209,6 +213,23 @@ class Engine:
         self._check(self._lib.nngp_loglik_device(self._h, int(kernel_id), ctypes.c_void_p(d_params), int(K),
                                                  ctypes.c_void_p(d_out), ctypes.c_void_p(stream or 0)),
                     "nngp_loglik_device")
+
+    def peer_export(self, K_cap=256):
+        """Allocates this rank's exchange buffer; returns its CUDA IPC handle (64 bytes)."""
+        buf = ctypes.create_string_buffer(IPC_HANDLE_BYTES)
+        self._check(self._lib.nngp_peer_export(self._h, int(K_cap), buf), "nngp_peer_export")
+        return buf.raw
+
+    def peer_connect(self, rank, world, handles):
+        """handles: the ranks' IPC handles concatenated in rank order (world * 64 bytes)."""
+        if len(handles) != world * IPC_HANDLE_BYTES:
+            raise ValueError("need world * 64 bytes of IPC handles")
+        self._check(self._lib.nngp_peer_connect(self._h, int(rank), int(world), bytes(handles)), "nngp_peer_connect")
+
+    def loglik_device_allreduce(self, kernel_id, d_params, K, d_out, stream=None):
+        self._check(self._lib.nngp_loglik_device_allreduce(self._h, int(kernel_id), ctypes.c_void_p(d_params), int(K),
+                                                           ctypes.c_void_p(d_out), ctypes.c_void_p(stream or 0)),
+                    "nngp_loglik_device_allreduce")
 
     def factors(self, kernel_id, params, i0=0, i1=None, want_B=True, want_F=True):
         i1 = self.n if i1 is None else i1

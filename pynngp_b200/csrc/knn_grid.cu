@@ -30,6 +30,7 @@
 #include <algorithm>
 
 #include "nngp_common.cuh"
+#include "peer_exchange.cuh"
 
 namespace nngp_grid {
 
@@ -474,4 +475,24 @@ cudaError_t launch_knn_grid(nngp_handle *h, bool ordered, int m, int64_t row_lo,
 #undef GRID_TRY
     *used = 1;
     return cudaSuccess;
+}
+
+// A rank with an empty shard still takes part in the statistics exchange: one block per parameter vector
+// publishes zeros and collects the sum (peer_exchange.cuh).
+__global__ void __launch_bounds__(32) peer_zero_kernel(PeerExchange px, double *out)
+{
+    __shared__ double sh[16];
+    double tot[3] = {0.0, 0.0, 0.0};
+    peer_allreduce3(px, blockIdx.x, 0.0, 0.0, 0.0, sh, tot);
+    if (threadIdx.x == 0) {
+        out[size_t(blockIdx.x) * 3 + 0] = tot[0];
+        out[size_t(blockIdx.x) * 3 + 1] = tot[1];
+        out[size_t(blockIdx.x) * 3 + 2] = tot[2];
+    }
+}
+
+cudaError_t launch_peer_zero(nngp_handle *, const PeerExchange &px, int K, double *d_out, cudaStream_t stream)
+{
+    peer_zero_kernel<<<K, 32, 0, stream>>>(px, d_out);
+    return cudaGetLastError();
 }

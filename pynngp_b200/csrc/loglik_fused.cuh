@@ -26,6 +26,7 @@
 #include <string.h>
 
 #include "nngp_common.cuh"
+#include "peer_exchange.cuh"
 
 namespace nngp_fused {
 
@@ -802,10 +803,15 @@ __global__ void __launch_bounds__(kThreads, MINB) fused_loglik_kernel(const Eval
             }
             __syncthreads();
         }
+        double tot[3] = {fin[0][0], fin[0][1], fin[0][2]};
+        if (a.px.world > 1) {  // sum over the ranks through NVLink peer memory (block-uniform branch)
+            __syncthreads();
+            peer_allreduce3(a.px, blockIdx.y, tot[0], tot[1], tot[2], &fin[kThreads / 2][0], tot);
+        }
         if (threadIdx.x == 0) {
-            a.out[size_t(blockIdx.y) * 3 + 0] = fin[0][0];
-            a.out[size_t(blockIdx.y) * 3 + 1] = fin[0][1];
-            a.out[size_t(blockIdx.y) * 3 + 2] = fin[0][2];
+            a.out[size_t(blockIdx.y) * 3 + 0] = tot[0];
+            a.out[size_t(blockIdx.y) * 3 + 1] = tot[1];
+            a.out[size_t(blockIdx.y) * 3 + 2] = tot[2];
             a.counters[blockIdx.y] = 0u;  // ready for the next launch
         }
     }

@@ -173,6 +173,9 @@ void nngp_destroy(nngp_handle *h)
     free_dev(h->pts); free_dev(h->eps2); free_dev(h->nbr);
     free_dev(h->d_params); free_dev(h->d_out); free_dev(h->d_partials);
     free_dev(h->d_counters); free_dev(h->d_tile_counter);
+    for (int r = 0; r < NNGP_MAX_PEERS; ++r)
+        if (h->peer_base[r] && h->peer_base[r] != h->xbuf) cudaIpcCloseMemHandle(h->peer_base[r]);
+    free_dev(h->xbuf);
     if (h->h_stage) cudaFreeHost(h->h_stage);
     cudaStreamDestroy(h->stream);
     delete h;
@@ -386,6 +389,87 @@ int nngp_loglik_device(nngp_handle *h, int kernel_id, const double *d_params, in
     a.lo = h->lo; a.hi = h->hi; a.m = h->m;
     a.params = d_params; a.partials = h->d_partials; a.counters = h->d_counters; a.out = d_out;
     a.emit = 0;
+    CUDA_TRY(h, family_launch(h->dtype, kernel_id, h->m, h->D, a, K, grid, st));
+    ++h->launches;
+    return NNGP_OK;
+}
+
+static size_t peer_slots_bytes(int K_cap) { return sizeof(double) * 2 * NNGP_MAX_PEERS * size_t(K_cap) * 3; }
+static size_t peer_flags_bytes(int K_cap) { return sizeof(unsigned long long) * 2 * NNGP_MAX_PEERS * size_t(K_cap); }
+
+int nngp_peer_export(nngp_handle *h, int K_cap, unsigned char *handle_out)
+{
+    if (!h) return fail(nullptr, NNGP_EINVAL, "null handle");
+    if (!handle_out || K_cap < 1) return fail(h, NNGP_EINVAL, "need handle_out != NULL and K_cap >= 1");
+    if (h->px.world > 1) return fail(h, NNGP_ESTATE, "peer exchange is already connected");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    free_dev(h->xbuf);
+    const size_t bytes = peer_slots_bytes(K_cap) + peer_flags_bytes(K_cap);
+    CUDA_TRY(h, cudaMalloc(&h->xbuf, bytes));
+    CUDA_TRY(h, cudaMemset(h->xbuf, 0, bytes));
+    CUDA_TRY(h, cudaDeviceSynchronize());
+    h->px.K_cap = K_cap;
+    cudaIpcMemHandle_t ih;
+    CUDA_TRY(h, cudaIpcGetMemHandle(&ih, h->xbuf));
+    static_assert(sizeof(ih) == NNGP_IPC_HANDLE_BYTES, "cudaIpcMemHandle_t size");
+    memcpy(handle_out, &ih, sizeof(ih));
+    return NNGP_OK;
+}
+
+int nngp_peer_connect(nngp_handle *h, int rank, int world, const unsigned char *handles)
+{
+    if (!h) return fail(nullptr, NNGP_EINVAL, "null handle");
+    if (!h->xbuf) return fail(h, NNGP_ESTATE, "call nngp_peer_export first");
+    if (!handles || world < 2 || world > NNGP_MAX_PEERS || rank < 0 || rank >= world)
+        return fail(h, NNGP_EINVAL, "need 2 <= world <= 8, 0 <= rank < world and world handles");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    for (int r = 0; r < world; ++r) {
+        void *base = h->xbuf;
+        if (r != rank) {
+            cudaIpcMemHandle_t ih;
+            memcpy(&ih, handles + size_t(r) * NNGP_IPC_HANDLE_BYTES, sizeof(ih));
+            cudaError_t e = cudaIpcOpenMemHandle(&base, ih, cudaIpcMemLazyEnablePeerAccess);
+            if (e != cudaSuccess) {
+                for (int q = 0; q < r; ++q)
+                    if (h->peer_base[q] && h->peer_base[q] != h->xbuf) { cudaIpcCloseMemHandle(h->peer_base[q]); h->peer_base[q] = nullptr; }
+                return cuda_fail(h, e, "cudaIpcOpenMemHandle (peers must be GPUs of one node with P2P access)");
+            }
+        }
+        h->peer_base[r] = base;
+        h->px.slots[r] = reinterpret_cast<double *>(base);
+        h->px.flags[r] = reinterpret_cast<unsigned long long *>(static_cast<char *>(base) + peer_slots_bytes(h->px.K_cap));
+    }
+    h->px.rank = rank;
+    h->px.world = world;
+    h->px.gen = 0;
+    return NNGP_OK;
+}
+
+int nngp_loglik_device_allreduce(nngp_handle *h, int kernel_id, const double *d_params, int K, double *d_out, void *stream)
+{
+    int rc = check_eval(h, kernel_id, d_params, K);
+    if (rc) return rc;
+    if (!d_out) return fail(h, NNGP_EINVAL, "d_out must not be NULL");
+    if (h->px.world < 2) return fail(h, NNGP_ESTATE, "peer exchange is not connected (nngp_peer_export / nngp_peer_connect)");
+    if (K > h->px.K_cap) return fail(h, NNGP_EINVAL, "K exceeds the exchange buffer's K_cap");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+    PeerExchange px = h->px;
+    px.gen = ++h->px.gen;  // every rank issues the same sequence of exchanges
+    const int64_t nloc = h->hi - h->lo;
+    if (nloc == 0) {
+        CUDA_TRY(h, launch_peer_zero(h, px, K, d_out, st));
+        ++h->launches;
+        return NNGP_OK;
+    }
+    const int grid = grid_for(h, kernel_id, nloc);
+    if ((rc = ensure_scratch(h, K, grid))) return rc;
+    EvalArgs a{};
+    a.pts = h->pts; a.eps2 = h->eps2; a.nbr = h->nbr;
+    a.lo = h->lo; a.hi = h->hi; a.m = h->m;
+    a.params = d_params; a.partials = h->d_partials; a.counters = h->d_counters; a.out = d_out;
+    a.emit = 0;
+    a.px = px;
     CUDA_TRY(h, family_launch(h->dtype, kernel_id, h->m, h->D, a, K, grid, st));
     ++h->launches;
     return NNGP_OK;

@@ -16,6 +16,18 @@
 
 #include "../../include/nngp_b200.h"
 
+// Cross-GPU exchange of the K x 3 statistics over NVLink peer memory (one process per GPU, buffers
+// shared through CUDA IPC).  Every rank owns one exchange buffer:
+//   slots [2][NNGP_MAX_PEERS][K_cap * 3] doubles, then flags [2][NNGP_MAX_PEERS][K_cap] generations;
+// the leading index is the parity of the exchange generation, the second the WRITING rank.
+constexpr int NNGP_MAX_PEERS = 8;
+struct PeerExchange {
+    int world = 0, rank = 0, K_cap = 0;
+    unsigned long long gen = 0;                  // this launch's generation (>= 1), same on all ranks
+    double *slots[NNGP_MAX_PEERS] = {};          // rank r's buffer as mapped in this process
+    unsigned long long *flags[NNGP_MAX_PEERS] = {};
+};
+
 struct nngp_handle {
     int device = 0;
     int dtype = NNGP_F64;
@@ -47,6 +59,11 @@ struct nngp_handle {
     unsigned int *d_tile_counter = nullptr;
     double *h_stage = nullptr;     // pinned: K_cap x (4 + 3)
 
+    // peer exchange (multi-GPU): own buffer, peers' buffers opened through CUDA IPC
+    void *xbuf = nullptr;
+    void *peer_base[NNGP_MAX_PEERS] = {};
+    PeerExchange px;
+
     int64_t launches = 0;
     std::string err;
 };
@@ -65,6 +82,7 @@ struct EvalArgs {
     // optional per-location outputs (rows lo..hi map to output rows 0..hi-lo); any may be null
     int emit;                 // 0: reduction only
     double *B, *F, *CN, *cc, *cs;
+    PeerExchange px;          // world > 1: `out` receives the sum over all ranks (see peer_allreduce3)
 };
 
 // launchers implemented in the .cu files; each returns the cudaError of the launch.
@@ -82,4 +100,6 @@ cudaError_t launch_knn_brute_rows(nngp_handle *h, int m, int64_t first_row, int6
 // the data does not suit a grid
 cudaError_t launch_knn_grid(nngp_handle *h, bool ordered, int m, int64_t row_lo, int64_t row_hi, int64_t cand_cap,
                             int32_t *table, cudaStream_t stream, int force, int *used);
+// publishes zeros for a rank whose shard is empty (it still takes part in the exchange)
+cudaError_t launch_peer_zero(nngp_handle *h, const PeerExchange &px, int K, double *d_out, cudaStream_t stream);
 cudaError_t launch_fma_peak(nngp_handle *h, int dtype, int iters, double *instr_per_s);

@@ -74,12 +74,48 @@ class NNGP(object):
         self._make_s_neighbor_sets(neighbors)
         self._make_t_neighbor_sets()
         self._ws = None
+        self._peer_ok = self._setup_peer_exchange()
 
     # ---- construction steps, named as in the reference -----------------------------------------
     def _local_device(self):
         import os
 
         return int(os.environ.get("LOCAL_RANK", "0")) if self._world > 1 else 0
+
+    def _setup_peer_exchange(self, K_cap=256):
+        """Multi-GPU on one node: map every rank's exchange buffer (CUDA IPC) so the fused kernel sums the
+        statistics over NVLink peer memory itself (nngp_loglik_device_allreduce).  Any failure on any rank
+        -- ranks on different nodes, no P2P, NNGP_PEER_EXCHANGE=0 -- leaves all ranks on the NCCL allreduce."""
+        import os
+
+        if self._world < 2:
+            return False
+        import torch
+        import torch.distributed as dist
+
+        if self._world > 8 or dist.get_backend(self._group) != "nccl":
+            return False
+        dev = torch.device("cuda", self._engine.device)
+        ok = os.environ.get("NNGP_PEER_EXCHANGE", "1") != "0"
+        mine = torch.zeros(_lib.IPC_HANDLE_BYTES, dtype=torch.uint8, device=dev)
+        if ok:
+            try:
+                mine = torch.frombuffer(bytearray(self._engine.peer_export(K_cap)), dtype=torch.uint8).to(dev)
+            except _lib.NNGPError:
+                ok = False
+        allh = [torch.empty_like(mine) for _ in range(self._world)]
+        dist.all_gather(allh, mine, group=self._group)
+        flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self._group)
+        if int(flag.item()) == 1:
+            try:
+                self._engine.peer_connect(self._rank, self._world, b"".join(bytes(h.cpu().numpy().tobytes()) for h in allh))
+            except _lib.NNGPError:
+                ok = False
+            flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self._group)
+        self._peer_K_cap = K_cap
+        return int(flag.item()) == 1
 
     def _init_s(self):
         # nngp.py:21-40.  Only 'S=T' works upstream (the tuple branches read an unset attribute,
@@ -248,31 +284,52 @@ class NNGP(object):
         return total
 
     def _loglik_batch_sharded(self, params):
-        """Multi-GPU evaluation with no host round trip between the kernel and the collective: the
-        fused kernel writes this rank's (K, 3) partial statistics into a torch CUDA tensor on torch's
-        current stream, NCCL sums them over NVLink on the same stream, one D2H copy returns them."""
+        """Multi-GPU evaluation with no host round trip between the kernel and the exchange: parameters go
+        up from a pinned buffer, the fused kernel writes the (K, 3) statistics -- already summed over the
+        ranks through NVLink peer memory, or this rank's partials followed by an NCCL allreduce on the
+        same stream when the peer exchange is unavailable -- and one pinned D2H copy returns them."""
         import torch
 
         dev = torch.device("cuda", self._engine.device)
         K = params.shape[0]
-        with torch.cuda.device(dev):
-            stream = torch.cuda.current_stream()
-            if stream.cuda_stream == 0:  # the C ABI reads NULL as "the handle's stream": use a real one
-                if getattr(self, "_stream", None) is None:
-                    self._stream = torch.cuda.Stream()
-                stream = self._stream
-            with torch.cuda.stream(stream):
-                d_prm = torch.from_numpy(params).to(dev, non_blocking=True)
-                total = torch.zeros((K, _lib.NSTAT), dtype=torch.float64, device=dev)
-                d_out = torch.empty_like(total)
-                for c in range(self._y2d.shape[1]):
-                    self._set_column(c)
-                    self._engine.loglik_device(self._kernel.kernel_id, d_prm.data_ptr(), K, d_out.data_ptr(),
+        buf = getattr(self, "_shard_bufs", None)
+        if buf is None or buf["K"] < K:
+            with torch.cuda.device(dev):
+                cap = max(K, 16)
+                buf = self._shard_bufs = {
+                    "K": cap, "stream": torch.cuda.Stream(),
+                    "h_prm": torch.empty((cap, _lib.NPARAM), dtype=torch.float64).pin_memory(),
+                    "h_out": torch.empty((cap, _lib.NSTAT), dtype=torch.float64).pin_memory(),
+                    "d_prm": torch.empty((cap, _lib.NPARAM), dtype=torch.float64, device=dev),
+                    "d_out": torch.empty((cap, _lib.NSTAT), dtype=torch.float64, device=dev),
+                    "d_tot": torch.empty((cap, _lib.NSTAT), dtype=torch.float64, device=dev),
+                }
+        stream = buf["stream"]
+        ncol = self._y2d.shape[1]
+        fused = self._peer_ok and K <= self._peer_K_cap
+        buf["h_prm"][:K].numpy()[...] = params
+        with torch.cuda.device(dev), torch.cuda.stream(stream):
+            d_prm, d_out, d_tot = buf["d_prm"][:K], buf["d_out"][:K], buf["d_tot"][:K]
+            d_prm.copy_(buf["h_prm"][:K], non_blocking=True)
+            for c in range(ncol):
+                if ncol > 1:
+                    stream.synchronize()  # the previous column's kernel still reads the y it is about to replace
+                self._set_column(c)
+                dst = d_out if ncol == 1 else d_tot if c == 0 else d_out
+                if fused:  # the kernel's last block sums over the ranks through NVLink peer memory
+                    self._engine.loglik_device_allreduce(self._kernel.kernel_id, d_prm.data_ptr(), K, dst.data_ptr(),
+                                                         stream.cuda_stream)
+                else:
+                    self._engine.loglik_device(self._kernel.kernel_id, d_prm.data_ptr(), K, dst.data_ptr(),
                                                stream.cuda_stream)
-                    total += d_out
-                _dist.allreduce_stats(total, self._group)
-                out = total.cpu().numpy()
-        return out
+                if c > 0:
+                    d_tot += d_out
+            res = d_out if ncol == 1 else d_tot
+            if not fused:
+                _dist.allreduce_stats(res, self._group)
+            buf["h_out"][:K].copy_(res, non_blocking=True)
+            stream.synchronize()
+        return buf["h_out"][:K].numpy().copy()
 
     def loglik_terms(self, sigma2=None, phi=None, tau2=None):
         """(sum_i log F_i, sum_i r_i^2 / F_i) -- the reduction BASELINE.json's north_star names."""

@@ -23,6 +23,16 @@ s, y = synthetic(c["n"], c["D"], c["seed"])
 spec = Matern(1.5, **PARAMS)
 model = NNGP(s, y, 0.0, "S=T", c["m"], spec, device=local)          # sharded: knn split + MAX-assemble
 terms = model.loglik_terms()
+# the fused peer-memory exchange against the NCCL allreduce: same totals (summation order differs)
+peer = model._peer_ok
+model._peer_ok = False
+terms_nccl = model.loglik_terms()
+model._peer_ok = peer
+np.testing.assert_allclose(terms, terms_nccl, rtol=1e-13)
+batch = model.loglik_batch(np.array([[1.0, 6.0, 0.1], [1.5, 9.0, 0.2], [0.7, 4.0, 0.05]]))
+allb = [None] * dist.get_world_size()
+dist.all_gather_object(allb, batch.tobytes())
+assert all(b == allb[0] for b in allb), "ranks disagree on the exchanged totals"
 if rank == 0:
     e = _lib.Engine(local)                                              # single-GPU reference on rank 0
     e.set_data(s, y)
@@ -30,6 +40,6 @@ if rank == 0:
     assert np.array_equal(e.get_neighbors(), model._table), "assembled neighbour table differs"
     one = e.loglik(1, np.array([PARAMS["sigma2"], PARAMS["phi"], PARAMS["tau2"], 0.0]))[0]
     np.testing.assert_allclose(terms, one[:2], rtol=1e-12)
-    print(f"multi-gpu ok: world={world} n={c['n']} m={c['m']} D={c['D']} terms={terms} knn_s={model._timings['knn_s']:.3f}")
+    print(f"multi-gpu ok: world={world} n={c['n']} m={c['m']} D={c['D']} peer_exchange={peer} terms={terms} knn_s={model._timings['knn_s']:.3f}")
 dist.barrier()
 dist.destroy_process_group()
