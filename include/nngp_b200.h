@@ -132,6 +132,8 @@ int nngp_peer_export(nngp_handle *h, int K_cap, unsigned char *handle_out);
 int nngp_peer_connect(nngp_handle *h, int rank, int world, const unsigned char *handles);
 int nngp_loglik_device_allreduce(nngp_handle *h, int kernel_id, const double *d_params, int K,
                                  double *d_out, void *stream);
+/* Host-pointer form (synchronous, like nngp_loglik): out receives the K x 3 totals over all ranks. */
+int nngp_loglik_allreduce(nngp_handle *h, int kernel_id, const double *params, int K, double *out);
 
 /* Per-location factors for rows [i0, i1) (any rows, not only the shard): B (i1-i0) x m fp64
  * (b_i = C_N(i)^-1 c_i, zero padded; _Bsi nngp.py:73-76), F (i1-i0) (_Fsi nngp.py:88-90).

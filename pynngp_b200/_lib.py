@@ -48,6 +48,7 @@ SIGNATURES = {
     "nngp_peer_export": (ctypes.c_int, [_handle_p, ctypes.c_int, ctypes.c_char_p]),
     "nngp_peer_connect": (ctypes.c_int, [_handle_p, ctypes.c_int, ctypes.c_int, ctypes.c_char_p]),
     "nngp_loglik_device_allreduce": (ctypes.c_int, [_handle_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]),
+    "nngp_loglik_allreduce": (ctypes.c_int, [_handle_p, ctypes.c_int, _c_double_p, ctypes.c_int, _c_double_p]),
     "nngp_factors": (ctypes.c_int, [_handle_p, ctypes.c_int, _c_double_p, ctypes.c_int64, ctypes.c_int64, _c_double_p, _c_double_p]),
     "nngp_cov_blocks": (ctypes.c_int, [_handle_p, ctypes.c_int, _c_double_p, ctypes.c_int64, ctypes.c_int64, _c_double_p, _c_double_p, _c_double_p]),
     "nngp_launch_count": (ctypes.c_int64, [_handle_p]),
@@ -207,6 +208,16 @@ class Engine:
         out = np.empty((params.shape[0], NSTAT), dtype=np.float64)
         self._check(self._lib.nngp_loglik(self._h, int(kernel_id), _dp(params), params.shape[0], _dp(out)),
                     "nngp_loglik")
+        return out
+
+    def loglik_allreduce(self, kernel_id, params):
+        """Like loglik, but the (K, 3) result is the total over all ranks (fused peer-memory exchange)."""
+        params = _f64(params)
+        if params.ndim == 1:
+            params = params[None, :]
+        out = np.empty((params.shape[0], NSTAT), dtype=np.float64)
+        self._check(self._lib.nngp_loglik_allreduce(self._h, int(kernel_id), _dp(params), params.shape[0], _dp(out)),
+                    "nngp_loglik_allreduce")
         return out
 
     def loglik_device(self, kernel_id, d_params, K, d_out, stream=None):

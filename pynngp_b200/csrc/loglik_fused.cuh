@@ -374,8 +374,8 @@ __global__ void __launch_bounds__(kThreads, MINB) fused_loglik_kernel(const Eval
     const double diag0 = prm[0] + prm[2];
     const int m = a.m;
     constexpr int TB = exp_tab_bits<G, BUILD>();
-    if constexpr (sizeof(T) == 8)
-        for (int k = threadIdx.x; k < (1 << TB); k += kThreads) exp_tab[k] = T(prm[0] * exp2(double(k) / (1 << TB)));
+    if constexpr (sizeof(T) == 8)  // sigma2 * 2^(k / 2^TB) from the handle's table of 2^(j/2048): one L2 load and a multiply
+        for (int k = threadIdx.x; k < (1 << TB); k += kThreads) exp_tab[k] = T(prm[0] * __ldg(a.exp2tab + (k << (11 - TB))));
     // sum log F is carried as log(prod of mantissas) + ln2 * (sum of exponents): one multiply and a few
     // integer operations per location instead of a log() the whole warp would issue for one lane in G
     int nbad = 0;

@@ -161,6 +161,17 @@ int nngp_create(nngp_handle **out, int device, int dtype)
         delete h;
         return cuda_fail(nullptr, e, "cudaMalloc");
     }
+    {   // parameter-independent part of the covariance build's exp table: 2^(j/2048), j < 2048
+        std::vector<double> tab(2048);
+        for (int j = 0; j < 2048; ++j) tab[j] = exp2(double(j) / 2048.0);
+        if ((e = cudaMalloc(&h->d_exp2tab, sizeof(double) * 2048)) != cudaSuccess ||
+            (e = cudaMemcpy(h->d_exp2tab, tab.data(), sizeof(double) * 2048, cudaMemcpyHostToDevice)) != cudaSuccess) {
+            cudaFree(h->d_tile_counter);
+            cudaStreamDestroy(h->stream);
+            delete h;
+            return cuda_fail(nullptr, e, "cudaMalloc");
+        }
+    }
     *out = h;
     return NNGP_OK;
 }
@@ -172,7 +183,7 @@ void nngp_destroy(nngp_handle *h)
     cudaStreamSynchronize(h->stream);
     free_dev(h->pts); free_dev(h->eps2); free_dev(h->nbr);
     free_dev(h->d_params); free_dev(h->d_out); free_dev(h->d_partials);
-    free_dev(h->d_counters); free_dev(h->d_tile_counter);
+    free_dev(h->d_counters); free_dev(h->d_tile_counter); free_dev(h->d_exp2tab);
     for (int r = 0; r < NNGP_MAX_PEERS; ++r)
         if (h->peer_base[r] && h->peer_base[r] != h->xbuf) cudaIpcCloseMemHandle(h->peer_base[r]);
     free_dev(h->xbuf);
@@ -388,7 +399,7 @@ int nngp_loglik_device(nngp_handle *h, int kernel_id, const double *d_params, in
     a.pts = h->pts; a.eps2 = h->eps2; a.nbr = h->nbr;
     a.lo = h->lo; a.hi = h->hi; a.m = h->m;
     a.params = d_params; a.partials = h->d_partials; a.counters = h->d_counters; a.out = d_out;
-    a.emit = 0;
+    a.emit = 0; a.exp2tab = h->d_exp2tab;
     CUDA_TRY(h, family_launch(h->dtype, kernel_id, h->m, h->D, a, K, grid, st));
     ++h->launches;
     return NNGP_OK;
@@ -468,14 +479,14 @@ int nngp_loglik_device_allreduce(nngp_handle *h, int kernel_id, const double *d_
     a.pts = h->pts; a.eps2 = h->eps2; a.nbr = h->nbr;
     a.lo = h->lo; a.hi = h->hi; a.m = h->m;
     a.params = d_params; a.partials = h->d_partials; a.counters = h->d_counters; a.out = d_out;
-    a.emit = 0;
+    a.emit = 0; a.exp2tab = h->d_exp2tab;
     a.px = px;
     CUDA_TRY(h, family_launch(h->dtype, kernel_id, h->m, h->D, a, K, grid, st));
     ++h->launches;
     return NNGP_OK;
 }
 
-int nngp_loglik(nngp_handle *h, int kernel_id, const double *params, int K, double *out)
+static int loglik_host(nngp_handle *h, int kernel_id, const double *params, int K, double *out, bool allreduce)
 {
     int rc = check_eval(h, kernel_id, params, K);
     if (rc) return rc;
@@ -485,11 +496,23 @@ int nngp_loglik(nngp_handle *h, int kernel_id, const double *params, int K, doub
     double *hp = h->h_stage, *ho = h->h_stage + size_t(NNGP_NPARAM) * h->K_cap;
     memcpy(hp, params, sizeof(double) * NNGP_NPARAM * K);
     CUDA_TRY(h, cudaMemcpyAsync(h->d_params, hp, sizeof(double) * NNGP_NPARAM * K, cudaMemcpyHostToDevice, h->stream));
-    if ((rc = nngp_loglik_device(h, kernel_id, h->d_params, K, h->d_out, h->stream))) return rc;
+    rc = allreduce ? nngp_loglik_device_allreduce(h, kernel_id, h->d_params, K, h->d_out, h->stream)
+                   : nngp_loglik_device(h, kernel_id, h->d_params, K, h->d_out, h->stream);
+    if (rc) return rc;
     CUDA_TRY(h, cudaMemcpyAsync(ho, h->d_out, sizeof(double) * NNGP_NSTAT * K, cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     memcpy(out, ho, sizeof(double) * NNGP_NSTAT * K);
     return NNGP_OK;
+}
+
+int nngp_loglik(nngp_handle *h, int kernel_id, const double *params, int K, double *out)
+{
+    return loglik_host(h, kernel_id, params, K, out, false);
+}
+
+int nngp_loglik_allreduce(nngp_handle *h, int kernel_id, const double *params, int K, double *out)
+{
+    return loglik_host(h, kernel_id, params, K, out, true);
 }
 
 // shared by nngp_factors / nngp_cov_blocks: run the emitting variant over [i0, i1) in slabs
@@ -526,7 +549,7 @@ static int run_emit(nngp_handle *h, int kernel_id, const double *params, int64_t
         a.pts = h->pts; a.eps2 = h->eps2; a.nbr = h->nbr;
         a.lo = s0; a.hi = s1; a.m = m;
         a.params = h->d_params; a.partials = h->d_partials; a.counters = h->d_counters; a.out = h->d_out;
-        a.emit = 1; a.B = dB; a.F = dF; a.CN = dCN; a.cc = dcc; a.cs = dcs;
+        a.emit = 1; a.exp2tab = h->d_exp2tab; a.B = dB; a.F = dF; a.CN = dCN; a.cc = dcc; a.cs = dcs;
         if (dCN) EMIT_TRY(cudaMemsetAsync(dCN, 0, sizeof(double) * cnt * m * m, h->stream));
         if (dcc) EMIT_TRY(cudaMemsetAsync(dcc, 0, sizeof(double) * cnt * m, h->stream));
         EMIT_TRY(family_launch(h->dtype, kernel_id, m, h->D, a, 1, grid_for(h, kernel_id, cnt), h->stream));

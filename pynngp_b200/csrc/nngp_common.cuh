@@ -57,6 +57,7 @@ struct nngp_handle {
     double *d_partials = nullptr;  // K_cap x grid_cap x 3
     unsigned int *d_counters = nullptr;  // K_cap tickets for the last-block reduction
     unsigned int *d_tile_counter = nullptr;
+    double *d_exp2tab = nullptr;   // 2^(j/2048), j < 2048 (built once at nngp_create)
     double *h_stage = nullptr;     // pinned: K_cap x (4 + 3)
 
     // peer exchange (multi-GPU): own buffer, peers' buffers opened through CUDA IPC
@@ -76,6 +77,7 @@ struct EvalArgs {
     int64_t lo, hi;       // rows to evaluate
     int m;
     const double *params;     // gridDim.y x 4 (device)
+    const double *exp2tab;    // 2^(j/2048), j < 2048
     double *partials;         // gridDim.y x gridDim.x x 3
     unsigned int *counters;   // gridDim.y
     double *out;              // gridDim.y x 3

@@ -284,14 +284,21 @@ class NNGP(object):
         return total
 
     def _loglik_batch_sharded(self, params):
-        """Multi-GPU evaluation with no host round trip between the kernel and the exchange: parameters go
-        up from a pinned buffer, the fused kernel writes the (K, 3) statistics -- already summed over the
-        ranks through NVLink peer memory, or this rank's partials followed by an NCCL allreduce on the
-        same stream when the peer exchange is unavailable -- and one pinned D2H copy returns them."""
+        """Multi-GPU evaluation.  With the peer exchange connected the fused kernel itself returns the
+        statistics summed over the ranks (NVLink peer memory).  Otherwise: parameters go up from a pinned
+        buffer, the kernel writes this rank's partials, an NCCL allreduce follows on the same stream with no
+        host round trip in between, and one pinned D2H copy returns the totals."""
+        K = params.shape[0]
+        if self._peer_ok and K <= self._peer_K_cap:
+            # the kernel's last block sums over the ranks through NVLink peer memory: no torch, no NCCL
+            total = np.zeros((K, _lib.NSTAT))
+            for c in range(self._y2d.shape[1]):
+                self._set_column(c)
+                total += self._engine.loglik_allreduce(self._kernel.kernel_id, params)
+            return total
         import torch
 
         dev = torch.device("cuda", self._engine.device)
-        K = params.shape[0]
         buf = getattr(self, "_shard_bufs", None)
         if buf is None or buf["K"] < K:
             with torch.cuda.device(dev):
@@ -306,7 +313,6 @@ class NNGP(object):
                 }
         stream = buf["stream"]
         ncol = self._y2d.shape[1]
-        fused = self._peer_ok and K <= self._peer_K_cap
         buf["h_prm"][:K].numpy()[...] = params
         with torch.cuda.device(dev), torch.cuda.stream(stream):
             d_prm, d_out, d_tot = buf["d_prm"][:K], buf["d_out"][:K], buf["d_tot"][:K]
@@ -316,17 +322,12 @@ class NNGP(object):
                     stream.synchronize()  # the previous column's kernel still reads the y it is about to replace
                 self._set_column(c)
                 dst = d_out if ncol == 1 else d_tot if c == 0 else d_out
-                if fused:  # the kernel's last block sums over the ranks through NVLink peer memory
-                    self._engine.loglik_device_allreduce(self._kernel.kernel_id, d_prm.data_ptr(), K, dst.data_ptr(),
-                                                         stream.cuda_stream)
-                else:
-                    self._engine.loglik_device(self._kernel.kernel_id, d_prm.data_ptr(), K, dst.data_ptr(),
-                                               stream.cuda_stream)
+                self._engine.loglik_device(self._kernel.kernel_id, d_prm.data_ptr(), K, dst.data_ptr(),
+                                           stream.cuda_stream)
                 if c > 0:
                     d_tot += d_out
             res = d_out if ncol == 1 else d_tot
-            if not fused:
-                _dist.allreduce_stats(res, self._group)
+            _dist.allreduce_stats(res, self._group)  # NCCL on the same stream
             buf["h_out"][:K].copy_(res, non_blocking=True)
             stream.synchronize()
         return buf["h_out"][:K].numpy().copy()
