@@ -848,7 +848,8 @@ int blocks_per_sm()
 //   m <=  7 : (4, 2) unrolled row-owner build
 //   m <= 15 : (4, 4) unrolled row-owner build, fp64: 6-pair batches, 255 registers, 8 warps/SM (in-thread
 //             parallelism hides the FP64 latency better than a third block of warps did: 0.433 vs 0.452 ms)
-//   m <= 31 : (8, 4) rolled pair-list build
+//   m <= 31 : (8, 4); fp64 3-D: unrolled row-owner build (5.96 vs 6.26 ms per 2e6 locations at m = 30), otherwise the
+//             rolled pair-list build (2-D: 5.12 vs 5.22 ms -- the unrolled form spills more there)
 //   m == 32 : (16, 3) rolled pair-list build
 // MINB = resident blocks per SM the kernel is compiled for (the register cap).
 struct ShapeInfo {
@@ -886,7 +887,7 @@ auto dispatch_shape(int m, const F &f)
 #endif
     if (m <= 7) return f.template run<4, 2, DIM3, 4, 0>();
     if (m <= 15) return f.template run<4, 4, DIM3, (F64 ? 2 : 4), (F64 ? 2 : 0)>();
-    if (m <= 31) return f.template run<8, 4, DIM3, (F64 ? 2 : 4), 1>();
+    if (m <= 31) return f.template run<8, 4, DIM3, (F64 ? 2 : 4), (F64 && DIM3 ? 0 : 1)>();
     return f.template run<16, 3, DIM3, (F64 ? 2 : 4), 1>();
 }
 

@@ -14,6 +14,9 @@ dtypes = sys.argv[2].split(",") if len(sys.argv) > 2 else ["float64"]
 c = dict(CONFIGS[name])
 if len(sys.argv) > 3:
     c["n"] = int(sys.argv[3])
+for key in ("D", "m"):  # overrides: TUNE_D=2 TUNE_M=30
+    if os.environ.get("TUNE_" + key.upper()):
+        c[key] = int(os.environ["TUNE_" + key.upper()])
 s, y = synthetic(c["n"], c["D"], c["seed"])
 kid = {"exponential": 0, "matern32": 1, "matern52": 2}[c["kernel"]]
 prm = torch.tensor([[PARAMS["sigma2"], PARAMS["phi"], PARAMS["tau2"], 0.0]], dtype=torch.float64, device="cuda")
