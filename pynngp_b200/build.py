@@ -19,7 +19,7 @@ OBJ_DIR = os.path.join(OUT_DIR, "obj")
 LIB = os.path.join(OUT_DIR, "libnngp_b200.so")
 
 SOURCES = [
-    "nngp_api.cu", "knn_ordered.cu", "knn_grid.cu", "fma_peak.cu",
+    "nngp_api.cu", "knn_ordered.cu", "knn_grid.cu", "pack.cu", "fma_peak.cu",
     "fused_f64_exp.cu", "fused_f64_m32.cu", "fused_f64_m52.cu",
     "fused_f32_exp.cu", "fused_f32_m32.cu", "fused_f32_m52.cu",
 ]

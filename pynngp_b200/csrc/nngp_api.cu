@@ -202,29 +202,28 @@ int nngp_set_data(nngp_handle *h, const double *coords, int64_t n, int D, const 
     free_dev(h->pts); free_dev(h->eps2); free_dev(h->nbr);
     h->has_nbr = false; h->m = 0;
     h->n = n; h->D = D; h->lo = 0; h->hi = n;
-    // pack {x, y, z, yval} records on the host, one upload
-    std::vector<double4> rec((size_t)n);
-    double bl[3] = {INFINITY, INFINITY, INFINITY}, bh[3] = {-INFINITY, -INFINITY, -INFINITY};
-    bool finite = true;
-    for (int64_t i = 0; i < n; ++i) {
-        const double *c = coords + i * D;
-        for (int d = 0; d < D; ++d) {  // bounding box for the grid search of stage 1
-            finite &= std::isfinite(c[d]);
-            bl[d] = c[d] < bl[d] ? c[d] : bl[d];
-            bh[d] = c[d] > bh[d] ? c[d] : bh[d];
-        }
-        // D < 3: the unused z slot carries eps2 so the fused kernel gathers one record per neighbour
-        rec[(size_t)i] = make_double4(c[0], D > 1 ? c[1] : 0.0, D > 2 ? c[2] : (eps2 ? eps2[i] : 0.0), y[i]);
+    // raw arrays up, packed into {x, y, z, yval} records on the device (pack.cu), which also reduces the
+    // bounding box for the grid search of stage 1
+    double *d_coords = nullptr, *d_y = nullptr, *d_e2 = nullptr;
+    auto cleanup = [&]() { free_dev(d_coords); free_dev(d_y); if (d_e2 != h->eps2) free_dev(d_e2); };
+#define SET_TRY(call)                                                          \
+    do {                                                                       \
+        cudaError_t e_ = (call);                                               \
+        if (e_ != cudaSuccess) { cleanup(); free_dev(h->eps2); free_dev(h->pts); return cuda_fail(h, e_, #call); }  \
+    } while (0)
+    SET_TRY(cudaMalloc(&h->pts, sizeof(double4) * (size_t)n));
+    SET_TRY(cudaMalloc(&d_coords, sizeof(double) * (size_t)n * D));
+    SET_TRY(cudaMalloc(&d_y, sizeof(double) * (size_t)n));
+    SET_TRY(cudaMemcpyAsync(d_coords, coords, sizeof(double) * (size_t)n * D, cudaMemcpyHostToDevice, h->stream));
+    SET_TRY(cudaMemcpyAsync(d_y, y, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, h->stream));
+    if (eps2) {
+        SET_TRY(cudaMalloc(&d_e2, sizeof(double) * (size_t)n));
+        SET_TRY(cudaMemcpyAsync(d_e2, eps2, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, h->stream));
+        if (D > 2) h->eps2 = d_e2;  // D = 3: kept as its own array; D < 3: folded into the records' z slot
     }
-    for (int d = 0; d < 3; ++d) { h->bb_lo[d] = d < D ? bl[d] : 0.0; h->bb_hi[d] = d < D ? bh[d] : 0.0; }
-    h->bb_finite = finite;
-    CUDA_TRY(h, cudaMalloc(&h->pts, sizeof(double4) * (size_t)n));
-    CUDA_TRY(h, cudaMemcpyAsync(h->pts, rec.data(), sizeof(double4) * (size_t)n, cudaMemcpyHostToDevice, h->stream));
-    if (eps2 && D > 2) {
-        CUDA_TRY(h, cudaMalloc(&h->eps2, sizeof(double) * (size_t)n));
-        CUDA_TRY(h, cudaMemcpyAsync(h->eps2, eps2, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, h->stream));
-    }
-    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    SET_TRY(launch_pack_records(h, d_coords, d_y, d_e2, h->stream));  // synchronises the stream
+#undef SET_TRY
+    cleanup();
     return NNGP_OK;
 }
 

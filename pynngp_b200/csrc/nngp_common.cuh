@@ -12,7 +12,9 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <algorithm>
 #include <string>
+#include <vector>
 
 #include "../../include/nngp_b200.h"
 
@@ -104,4 +106,7 @@ cudaError_t launch_knn_grid(nngp_handle *h, bool ordered, int m, int64_t row_lo,
                             int32_t *table, cudaStream_t stream, int force, int *used);
 // publishes zeros for a rank whose shard is empty (it still takes part in the exchange)
 cudaError_t launch_peer_zero(nngp_handle *h, const PeerExchange &px, int K, double *d_out, cudaStream_t stream);
+// device-side packing of the records + bounding box (pack.cu); synchronises `stream`
+cudaError_t launch_pack_records(nngp_handle *h, const double *d_coords, const double *d_y, const double *d_eps2,
+                                cudaStream_t stream);
 cudaError_t launch_fma_peak(nngp_handle *h, int dtype, int iters, double *instr_per_s);
