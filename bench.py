@@ -258,6 +258,37 @@ def run_ours(args, cfg):
     barrier()
     kern_ms = float(np.mean([ka.elapsed_time(kb) for ka, kb in kev]))
 
+    # ---- cfg5: a sweep of K parameter vectors in one launch (pair distances shared by the vectors) ----
+    from pynngp_b200.synthetic import sweep_params
+
+    Ks = 64
+    d_prmK = torch.tensor(sweep_params(Ks), dtype=torch.float64, device="cuda")
+    d_outK = torch.zeros((Ks, 3), dtype=torch.float64, device="cuda")
+
+    def sweep_device():
+        if fused_exchange:
+            eng.loglik_device_allreduce(kid, d_prmK.data_ptr(), Ks, d_outK.data_ptr(), stream.cuda_stream)
+        else:
+            eng.loglik_device(kid, d_prmK.data_ptr(), Ks, d_outK.data_ptr(), stream.cuda_stream)
+            if world > 1:
+                dist.all_reduce(d_outK)
+
+    sweep_device()
+    barrier()
+    sw = []
+    for _ in range(3):
+        flush.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        sweep_device()
+        b.record(stream)
+        barrier()
+        sw.append(a.elapsed_time(b))
+    sweep_t = torch.tensor([float(np.mean(sw))], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(sweep_t, op=dist.ReduceOp.MAX)
+    sweep_ms = float(sweep_t.item())
+
     # ---- end to end through the public API (host params in, host stats out, every step) ----------
     for _ in range(3):
         model.loglik_terms()
@@ -330,6 +361,8 @@ def run_ours(args, cfg):
     # parity spot check on the very numbers being timed (cheap: the sample's rows)
     ms_per_step = total_ms / args.steps
     cfgd = workload_config(cfg, world)
+    cfgd["sweep_cfg5"] = {"K": Ks, "ms_per_launch": sweep_ms, "ms_per_eval": sweep_ms / Ks, "evals_per_s": 1e3 * Ks / sweep_ms,
+                          "what": "K parameter vectors (synthetic.sweep_params) in ONE launch: distances built once per location"}
     cfgd["exchange"] = ("none (1 GPU)" if world == 1 else
                         "fused into the kernel: P2P stores over NVLink peer memory (CUDA IPC), no NCCL call" if fused_exchange
                         else "NCCL all_reduce of 3 doubles after the kernel")

@@ -166,12 +166,11 @@ __device__ __forceinline__ T cov_from_u(T u, const T *tab, T sigma2)
 // instruction stream interleaves B dependency chains (the per-pair chain is ~20 dependent FP64
 // operations; with 3 resident warps per scheduler a single chain leaves the FP64 pipe idle).
 // In: x[b] = u_b^2 > 0.  Out: x[b] = sigma2 * rho(u_b).
-template <int KERN, int B, int TB>
-__device__ __forceinline__ void cov_batch(double (&x)[B], const double *tab, double)
+// x[b] = u_b^2 > 0  ->  x[b] = u_b (MUFU.RSQ64H seed + third-order correction), B chains interleaved
+template <int B>
+__device__ __forceinline__ void sqrt_batch(double (&x)[B])
 {
-    double y0[B], t1[B], e[B], u[B], kd[B], r[B], qq[B], tv[B];
-    int ki[B];
-    const double shift = kCovC[2];  // second constant of a two-constant FMA: a register
+    double y0[B], t1[B], e[B];
 #pragma unroll
     for (int b = 0; b < B; ++b) asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y0[b]) : "d"(x[b]));
 #pragma unroll
@@ -183,15 +182,23 @@ __device__ __forceinline__ void cov_batch(double (&x)[B], const double *tab, dou
 #pragma unroll
     for (int b = 0; b < B; ++b) y0[b] = y0[b] * e[b];
 #pragma unroll
-    for (int b = 0; b < B; ++b) u[b] = fma(t1[b], y0[b], t1[b]);
+    for (int b = 0; b < B; ++b) x[b] = fma(t1[b], y0[b], t1[b]);
+}
+// x[b] = u_b >= 0  ->  x[b] = (table scale) * rho(u_b)
+template <int KERN, int B, int TB>
+__device__ __forceinline__ void corr_batch(double (&x)[B], const double *tab)
+{
+    double e[B], kd[B], r[B], qq[B], tv[B];
+    int ki[B];
+    const double shift = kCovC[2];  // second constant of a two-constant FMA: a register
 #pragma unroll
-    for (int b = 0; b < B; ++b) kd[b] = fma(u[b], kExpA[exp_slot<TB>()], shift);
+    for (int b = 0; b < B; ++b) kd[b] = fma(x[b], kExpA[exp_slot<TB>()], shift);
 #pragma unroll
     for (int b = 0; b < B; ++b) { ki[b] = __double2loint(kd[b]); kd[b] = kd[b] - shift; }
 #pragma unroll
     for (int b = 0; b < B; ++b) tv[b] = tab[ki[b] & ((1 << TB) - 1)];
 #pragma unroll
-    for (int b = 0; b < B; ++b) r[b] = fma(kd[b], kExpB[exp_slot<TB>()], -u[b]);
+    for (int b = 0; b < B; ++b) r[b] = fma(kd[b], kExpB[exp_slot<TB>()], -x[b]);
     if (TB == 11) {
 #pragma unroll
         for (int b = 0; b < B; ++b) qq[b] = fma(r[b], kCovC[7], 0.5);
@@ -219,14 +226,20 @@ __device__ __forceinline__ void cov_batch(double (&x)[B], const double *tab, dou
     for (int b = 0; b < B; ++b) {
         const int hi = __double2hiint(r[b]) + ((ki[b] >> TB) << 20);
         const double v = __hiloint2double(hi, __double2loint(r[b]));
-        e[b] = __double2hiint(u[b]) >= 0x40862000 ? 0.0 : v;
+        e[b] = __double2hiint(x[b]) >= 0x40862000 ? 0.0 : v;
     }
 #pragma unroll
     for (int b = 0; b < B; ++b) {
         if (KERN == NNGP_EXPONENTIAL) x[b] = e[b];
-        else if (KERN == NNGP_MATERN32) x[b] = fma(u[b], e[b], e[b]);
-        else x[b] = fma(u[b], fma(u[b], kCovC[8], 1.0), 1.0) * e[b];
+        else if (KERN == NNGP_MATERN32) x[b] = fma(x[b], e[b], e[b]);
+        else x[b] = fma(x[b], fma(x[b], kCovC[8], 1.0), 1.0) * e[b];
     }
+}
+template <int KERN, int B, int TB>
+__device__ __forceinline__ void cov_batch(double (&x)[B], const double *tab, double)
+{
+    sqrt_batch<B>(x);
+    corr_batch<KERN, B, TB>(x, tab);
 }
 template <int KERN, int B, int TB>
 __device__ __forceinline__ void cov_batch(float (&x)[B], const float *tab, float sigma2)
@@ -282,6 +295,16 @@ __host__ __device__ constexpr int pair_slot(int t)
     return (j + 1) / G + t;
 }
 
+// BUILD = 6: the sweep variant of the unrolled build.  A block evaluates a chunk of up to kSweepChunk
+// parameter vectors per location: the pair distances (d^2 and sqrt: 9 of the 17 FP64 instructions a
+// covariance entry costs) are computed once and kept in registers, and for every parameter vector only
+// the correlation function, the elimination and the accumulation run.  sigma2 is factored out
+// (C = sigma2 (R + delta I), delta_i = (tau2 + eps2_i) / sigma2): the exp table carries no parameter, and
+// sum log F = (n - n_bad) log sigma2 + sum log F', sum r^2/F = (sum r^2/F') / sigma2 are restored at the end.
+constexpr int kSweepChunk = 8;
+template <int BUILD>
+__host__ __device__ constexpr bool sweep_build() { return BUILD == 6; }
+
 template <int P>
 __host__ __device__ constexpr int tile_stride() { return (P * (P - 1) / 2 + 7) / 8 * 8 + 4; }
 
@@ -298,7 +321,9 @@ struct WarpSmem {
     static constexpr size_t e2 = DIM3 ? size_t(W) * P * sizeof(double) : 0;  // gathered eps2 (D = 3 only;
                                                                              // D < 3 records carry it in .z)
     static constexpr size_t idx = size_t(R) * 32 * sizeof(int);          // next group's neighbour indices
-    static constexpr size_t acc = size_t(3) * 32 * sizeof(double);       // per-lane partial sums
+    // per-lane partial sums: {mantissa product, sum r^2/F, exponent sum} (+ n_bad and one set per
+    // parameter vector of the chunk in the sweep variant)
+    static constexpr size_t acc = sweep_build<BUILD>() ? size_t(kSweepChunk) * 4 * 32 * sizeof(double) : size_t(3) * 32 * sizeof(double);
     static constexpr size_t tile = BUILD == 1 ? (size_t(W) * tile_stride<P>() * sizeof(T) + 15) / 16 * 16 : 0;  // pair-indexed tile
     // scaled coordinates during the build; the elimination's two column buffers afterwards
     static constexpr int col_stride = P + 2;  // elements per location: P column entries, w_k, pad (distinct banks per group)
@@ -368,19 +393,39 @@ __global__ void __launch_bounds__(kThreads, MINB) fused_loglik_kernel(const Eval
     T *colw = reinterpret_cast<T *>(wbase + WS::rec + WS::e2 + WS::idx + WS::acc + WS::tile);
     T *col_even = colw + g * WS::col_stride, *col_odd = colw + (W + g) * WS::col_stride;
 
-    const double *prm = a.params + size_t(blockIdx.y) * NNGP_NPARAM;
-    const T sigma2 = T(prm[0]);
-    const double phi = prm[1];
+    constexpr bool SWEEP = sweep_build<BUILD>();
+    static_assert(!SWEEP || (sizeof(T) == 8 && !EMIT && ELIM == 1), "the sweep variant is fp64, reduction only");
+    // sweep: blockIdx.y = chunk of parameter vectors [k0, k0 + kc); otherwise one vector per blockIdx.y
+    const int k0 = SWEEP ? int(blockIdx.y) * kSweepChunk : int(blockIdx.y);
+    const int kc = SWEEP ? (a.K - k0 < kSweepChunk ? a.K - k0 : kSweepChunk) : 1;
+    const double *prm = a.params + size_t(k0) * NNGP_NPARAM;
+    const T sigma2 = SWEEP ? T(1) : T(prm[0]);
+    const double phi = SWEEP ? 1.0 : prm[1];  // sweep: coordinates stay unscaled, u = phi_k * distance per vector
     const double diag0 = prm[0] + prm[2];
     const int m = a.m;
     constexpr int TB = exp_tab_bits<G, BUILD>();
     if constexpr (sizeof(T) == 8)  // sigma2 * 2^(k / 2^TB) from the handle's table of 2^(j/2048): one L2 load and a multiply
-        for (int k = threadIdx.x; k < (1 << TB); k += kThreads) exp_tab[k] = T(prm[0] * __ldg(a.exp2tab + (k << (11 - TB))));
+        for (int k = threadIdx.x; k < (1 << TB); k += kThreads)
+            exp_tab[k] = T(double(sigma2) * __ldg(a.exp2tab + (k << (11 - TB))));
     // sum log F is carried as log(prod of mantissas) + ln2 * (sum of exponents): one multiply and a few
     // integer operations per location instead of a log() the whole warp would issue for one lane in G
     int nbad = 0;
-    accbuf[0] = 1.0; accbuf[32] = 0.0; accbuf[64] = 0.0;  // mantissa product, sum r^2/F, exponent sum: rarely touched,
-                                                            // kept out of the register file
+    __shared__ double sw_prm[kSweepChunk][4];  // sweep: {phi, tau2 / sigma2, 1 / sigma2, log sigma2} per vector
+    if constexpr (SWEEP) {
+        if (threadIdx.x < kc) {
+            const double *pk = prm + threadIdx.x * NNGP_NPARAM;
+            sw_prm[threadIdx.x][0] = pk[1];
+            sw_prm[threadIdx.x][1] = pk[2] / pk[0];
+            sw_prm[threadIdx.x][2] = 1.0 / pk[0];
+            sw_prm[threadIdx.x][3] = log(pk[0]);
+        }
+        for (int kk = 0; kk < kSweepChunk; ++kk) {
+            accbuf[kk * 128] = 1.0; accbuf[kk * 128 + 32] = 0.0; accbuf[kk * 128 + 64] = 0.0; accbuf[kk * 128 + 96] = 0.0;
+        }
+    } else {
+        accbuf[0] = 1.0; accbuf[32] = 0.0; accbuf[64] = 0.0;  // mantissa product, sum r^2/F, exponent sum: rarely
+                                                                // touched, kept out of the register file
+    }
     // The launch's pair list: rows in play are the m neighbour rows and the location's own row P-1
     // (rows m .. P-2 are identity padding: their entries stay at the zero the tile is filled with).
     // Pair t -> packed {row a, column b, tile offset a(a-1)/2 + b}; lanes walk the list with stride G,
@@ -469,6 +514,7 @@ __global__ void __launch_bounds__(kThreads, MINB) fused_loglik_kernel(const Eval
         asm volatile("cp.async.wait_group 0;" ::: "memory");
         __syncwarp();
         T rx[R], ry[R], rz[R], w[R], dg[R];
+        T w0[R], e2r[R];  // sweep only: the untouched right-hand side and eps2 of the lane's rows
         bool valid[R];
         {
             const double2 *recs = reinterpret_cast<const double2 *>(recbuf);
@@ -493,6 +539,8 @@ __global__ void __launch_bounds__(kThreads, MINB) fused_loglik_kernel(const Eval
                 rz[s] = valid[s] ? T((v1.x - sz) * phi) : T(0);
                 w[s] = valid[s] ? T(v1.y) : T(0);
                 dg[s] = valid[s] ? T(diag0 + e2) : T(1);
+                w0[s] = w[s];
+                e2r[s] = T(e2);
                 Pt pt;
                 pt.x = rx[s]; pt.y = ry[s];
                 if constexpr (DIM3) { pt.z = rz[s]; pt.pad = T(0); }
@@ -506,6 +554,7 @@ __global__ void __launch_bounds__(kThreads, MINB) fused_loglik_kernel(const Eval
 
         // ---- stage 2: covariance build ------------------------------------------------------------
         T A[R][P];
+        [[maybe_unused]] T Dst[SWEEP ? G * R * (R + 1) / 2 - R : 1];  // sweep: the lane's pair distances
         if constexpr (BUILD == 1) {
         // A rolled loop over this lane's share of the pair list, CB pairs in lock step (independent
         // dependency chains: one chain cannot fill the FP64 pipe -- 8-cycle DFMA latency).  Operands
@@ -563,7 +612,7 @@ __global__ void __launch_bounds__(kThreads, MINB) fused_loglik_kernel(const Eval
             // out of parallelism on the late columns, which only the last row block needs) -- and the
             // results go straight to the row registers.
             // BUILD selects the unrolled build's batch width: 0 -> 4, 2 -> 6, 3 -> 9, 4 -> 12 pairs in lock step
-            constexpr int CB = BUILD == 0 ? 4 : BUILD == 2 ? 6 : BUILD == 3 ? 9 : 12;
+            constexpr int CB = BUILD == 0 ? 4 : (BUILD == 2 || BUILD == 6) ? 6 : BUILD == 3 ? 9 : 12;
             constexpr int NP = G * R * (R + 1) / 2 - R;  // sum over s of (s*G + G - 1)
 #pragma unroll
             for (int t0 = 0; t0 < NP; t0 += CB) {
@@ -576,6 +625,14 @@ __global__ void __launch_bounds__(kThreads, MINB) fused_loglik_kernel(const Eval
                     const T dx = rx[s] - cj.x, dy = ry[s] - cj.y;
                     d2[b] = t_fma(dy, dy, t_fma(dx, dx, tiny_seed<T>()));
                     if constexpr (DIM3) { const T dz = rz[s] - cj.z; d2[b] = t_fma(dz, dz, d2[b]); }
+                }
+                if constexpr (SWEEP) {
+                    // distances only: they serve every parameter vector of the chunk
+                    sqrt_batch<CB>(d2);
+#pragma unroll
+                    for (int b = 0; b < CB; ++b)
+                        if (t0 + b < NP) Dst[t0 + b] = d2[b];
+                    continue;
                 }
                 cov_batch<KERN, CB, TB>(d2, exp_tab, sigma2);
 #pragma unroll
@@ -612,6 +669,40 @@ __global__ void __launch_bounds__(kThreads, MINB) fused_loglik_kernel(const Eval
                     }
                 }
             }
+        }
+
+        // sweep: one pass of [covariances from the stored distances -> elimination -> accumulation] per
+        // parameter vector of the chunk; otherwise a single pass over the matrix built above
+#pragma unroll 1
+        for (int kk = 0; kk < (SWEEP ? kc : 1); ++kk) {
+        volatile double *ab = accbuf + (SWEEP ? kk * 128 : 0);
+        if constexpr (SWEEP) {
+            constexpr int CBs = 6;
+            constexpr int NP = G * R * (R + 1) / 2 - R;
+            const T phik = T(sw_prm[kk][0]), dlt = T(sw_prm[kk][1]), is2 = T(sw_prm[kk][2]);
+#pragma unroll
+            for (int s = 0; s < R; ++s) {
+                w[s] = w0[s];
+                dg[s] = valid[s] ? t_fma(e2r[s], is2, T(1) + dlt) : T(1);  // 1 + (tau2 + eps2) / sigma2
+            }
+#pragma unroll
+            for (int t0 = 0; t0 < NP; t0 += CBs) {
+                T x[CBs];
+#pragma unroll
+                for (int b = 0; b < CBs; ++b) x[b] = Dst[(t0 + b < NP) ? t0 + b : NP - 1] * phik;
+                corr_batch<KERN, CBs, TB>(x, exp_tab);
+#pragma unroll
+                for (int b = 0; b < CBs; ++b) {
+                    if (t0 + b < NP) {
+                        const int s = pair_slot<G, R>(t0 + b), j = pair_col<G, R>(t0 + b);
+                        T v = x[b];
+                        if (j >= s * G) v = (s * G + q == j) ? dg[s] : v;  // diagonal block only
+                        A[s][j] = v;
+                    }
+                }
+            }
+#pragma unroll
+            for (int s = 0; s < R; ++s) A[s][s * G + G - 1] = dg[s];
         }
 
         // ---- stage 3: LDL^T elimination with the right-hand side carried along -----------------
@@ -706,21 +797,21 @@ __global__ void __launch_bounds__(kThreads, MINB) fused_loglik_kernel(const Eval
             const double Fd = double(Flast);
             bad |= !(Fd < INFINITY);
             if (bad) {
-                ++nbad;
+                if constexpr (SWEEP) ab[96] += 1.0; else ++nbad;
             } else {
                 const int hi = __double2hiint(Fd);
                 if (hi >= 0x00100000) {
                     // F = mant * 2^e, mant in [1, 2); the running product stays in [1, 2) as well
                     const double mant = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(Fd));
-                    const double pr = accbuf[0] * mant;
+                    const double pr = ab[0] * mant;
                     const int ph = __double2hiint(pr);
                     const int carry = (ph >> 20) - 1023;  // 0 or 1
-                    accbuf[0] = __hiloint2double(ph - (carry << 20), __double2loint(pr));
-                    accbuf[64] += double((hi >> 20) - 1023 + carry);
+                    ab[0] = __hiloint2double(ph - (carry << 20), __double2loint(pr));
+                    ab[64] += double((hi >> 20) - 1023 + carry);
                 } else {
-                    accbuf[64] += log2(Fd);  // subnormal F: the exponent field is not usable
+                    ab[64] += log2(Fd);  // subnormal F: the exponent field is not usable
                 }
-                accbuf[32] = fma(double(rlast) * double(rlast), fast_rcp(Fd), accbuf[32]);
+                ab[32] = fma(double(rlast) * double(rlast), fast_rcp(Fd), ab[32]);
             }
         }
 
@@ -755,29 +846,36 @@ __global__ void __launch_bounds__(kThreads, MINB) fused_loglik_kernel(const Eval
                 __syncwarp();
             }
         }
+        if constexpr (SWEEP) __syncwarp();  // the column buffers are rewritten by the next parameter vector
+        }  // parameter vectors
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");  // drain copies issued for groups past the end
 
-    double acc_log = fma(accbuf[64], 0.6931471805599453094, log(accbuf[0])), acc_quad = accbuf[32];
     // ---- reduction: warp shuffle tree -> block -> per-block partial -> last block sums ------
-    double bad_d = double(nbad);
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) {
-        acc_log += __shfl_xor_sync(0xffffffffu, acc_log, off);
-        acc_quad += __shfl_xor_sync(0xffffffffu, acc_quad, off);
-        bad_d += __shfl_xor_sync(0xffffffffu, bad_d, off);
-    }
+    // (one pass per parameter vector of the chunk; a single pass outside the sweep variant)
     __shared__ double red[kWarps][3];
     __shared__ bool is_last;
-    if (lane == 0) { red[warp][0] = acc_log; red[warp][1] = acc_quad; red[warp][2] = bad_d; }
-    __syncthreads();
-    double *part = a.partials + size_t(blockIdx.y) * gridDim.x * 3;
+    for (int kk = 0; kk < kc; ++kk) {
+        volatile double *ab = accbuf + (SWEEP ? kk * 128 : 0);
+        double acc_log = fma(ab[64], 0.6931471805599453094, log(ab[0])), acc_quad = ab[32];
+        double bad_d = SWEEP ? ab[96] : double(nbad);
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            acc_log += __shfl_xor_sync(0xffffffffu, acc_log, off);
+            acc_quad += __shfl_xor_sync(0xffffffffu, acc_quad, off);
+            bad_d += __shfl_xor_sync(0xffffffffu, bad_d, off);
+        }
+        __syncthreads();  // red[] of the previous pass has been read
+        if (lane == 0) { red[warp][0] = acc_log; red[warp][1] = acc_quad; red[warp][2] = bad_d; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double *part = a.partials + (size_t(k0 + kk) * gridDim.x + blockIdx.x) * 3;
+            double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+            for (int wv = 0; wv < kWarps; ++wv) { s0 += red[wv][0]; s1 += red[wv][1]; s2 += red[wv][2]; }
+            part[0] = s0; part[1] = s1; part[2] = s2;
+        }
+    }
     if (threadIdx.x == 0) {
-        double s0 = 0.0, s1 = 0.0, s2 = 0.0;
-        for (int wv = 0; wv < kWarps; ++wv) { s0 += red[wv][0]; s1 += red[wv][1]; s2 += red[wv][2]; }
-        part[size_t(blockIdx.x) * 3 + 0] = s0;
-        part[size_t(blockIdx.x) * 3 + 1] = s1;
-        part[size_t(blockIdx.x) * 3 + 2] = s2;
         __threadfence();
         const unsigned int ticket = atomicAdd(a.counters + blockIdx.y, 1u);
         is_last = (ticket == gridDim.x - 1);
@@ -785,35 +883,44 @@ __global__ void __launch_bounds__(kThreads, MINB) fused_loglik_kernel(const Eval
     __syncthreads();
     if (is_last) {
         __threadfence();
-        double t0 = 0.0, t1 = 0.0, t2 = 0.0;
-        for (unsigned int b = threadIdx.x; b < gridDim.x; b += kThreads) {
-            t0 += __ldcg(part + size_t(b) * 3 + 0);
-            t1 += __ldcg(part + size_t(b) * 3 + 1);
-            t2 += __ldcg(part + size_t(b) * 3 + 2);
-        }
         double(*fin)[3] = reinterpret_cast<double(*)[3]>(smem_raw);  // main-loop buffers are dead here
-        __syncthreads();
-        fin[threadIdx.x][0] = t0; fin[threadIdx.x][1] = t1; fin[threadIdx.x][2] = t2;
-        __syncthreads();
-        for (int stride = kThreads / 2; stride > 0; stride >>= 1) {
-            if (threadIdx.x < stride) {
-                fin[threadIdx.x][0] += fin[threadIdx.x + stride][0];
-                fin[threadIdx.x][1] += fin[threadIdx.x + stride][1];
-                fin[threadIdx.x][2] += fin[threadIdx.x + stride][2];
+        for (int kk = 0; kk < kc; ++kk) {
+            const double *part = a.partials + size_t(k0 + kk) * gridDim.x * 3;
+            double t0 = 0.0, t1 = 0.0, t2 = 0.0;
+            for (unsigned int b = threadIdx.x; b < gridDim.x; b += kThreads) {
+                t0 += __ldcg(part + size_t(b) * 3 + 0);
+                t1 += __ldcg(part + size_t(b) * 3 + 1);
+                t2 += __ldcg(part + size_t(b) * 3 + 2);
             }
             __syncthreads();
-        }
-        double tot[3] = {fin[0][0], fin[0][1], fin[0][2]};
-        if (a.px.world > 1) {  // sum over the ranks through NVLink peer memory (block-uniform branch)
+            fin[threadIdx.x][0] = t0; fin[threadIdx.x][1] = t1; fin[threadIdx.x][2] = t2;
             __syncthreads();
-            peer_allreduce3(a.px, blockIdx.y, tot[0], tot[1], tot[2], &fin[kThreads / 2][0], tot);
+            for (int stride = kThreads / 2; stride > 0; stride >>= 1) {
+                if (threadIdx.x < stride) {
+                    fin[threadIdx.x][0] += fin[threadIdx.x + stride][0];
+                    fin[threadIdx.x][1] += fin[threadIdx.x + stride][1];
+                    fin[threadIdx.x][2] += fin[threadIdx.x + stride][2];
+                }
+                __syncthreads();
+            }
+            double tot[3] = {fin[0][0], fin[0][1], fin[0][2]};
+            if constexpr (SWEEP) {
+                // restore sigma2: F = sigma2 F' on the (n - n_bad) locations that entered the sums
+                const double good = double(a.hi - a.lo) - tot[2];
+                tot[0] = fma(good, sw_prm[kk][3], tot[0]);
+                tot[1] *= sw_prm[kk][2];
+            }
+            if (a.px.world > 1) {  // sum over the ranks through NVLink peer memory (block-uniform branch)
+                __syncthreads();
+                peer_allreduce3(a.px, k0 + kk, tot[0], tot[1], tot[2], &fin[kThreads / 2][0], tot);
+            }
+            if (threadIdx.x == 0) {
+                a.out[size_t(k0 + kk) * 3 + 0] = tot[0];
+                a.out[size_t(k0 + kk) * 3 + 1] = tot[1];
+                a.out[size_t(k0 + kk) * 3 + 2] = tot[2];
+            }
         }
-        if (threadIdx.x == 0) {
-            a.out[size_t(blockIdx.y) * 3 + 0] = tot[0];
-            a.out[size_t(blockIdx.y) * 3 + 1] = tot[1];
-            a.out[size_t(blockIdx.y) * 3 + 2] = tot[2];
-            a.counters[blockIdx.y] = 0u;  // ready for the next launch
-        }
+        if (threadIdx.x == 0) a.counters[blockIdx.y] = 0u;  // ready for the next launch
     }
 }
 
@@ -821,15 +928,17 @@ __global__ void __launch_bounds__(kThreads, MINB) fused_loglik_kernel(const Eval
 template <typename T, int G, int R, int KERN, bool DIM3, int MINB, int BUILD, int ELIM>
 cudaError_t launch_one(const EvalArgs &a, int K, int grid_x, cudaStream_t stream)
 {
-    auto kern = a.emit ? fused_loglik_kernel<T, G, R, KERN, DIM3, MINB, BUILD, ELIM, true>
-                       : fused_loglik_kernel<T, G, R, KERN, DIM3, MINB, BUILD, ELIM, false>;
+    auto kern = fused_loglik_kernel<T, G, R, KERN, DIM3, MINB, BUILD, ELIM, false>;
+    if constexpr (!sweep_build<BUILD>())
+        if (a.emit) kern = fused_loglik_kernel<T, G, R, KERN, DIM3, MINB, BUILD, ELIM, true>;
     const size_t smem = smem_bytes<T, G, R, DIM3, BUILD>(a.emit != 0);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
 #ifdef NNGP_TUNE
     if (const char *c = getenv("NNGP_TUNE_CARVEOUT")) cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(c));
 #endif
-    kern<<<dim3(grid_x, K, 1), kThreads, smem, stream>>>(a);
+    const int grid_y = sweep_build<BUILD>() ? (K + kSweepChunk - 1) / kSweepChunk : K;
+    kern<<<dim3(grid_x, grid_y, 1), kThreads, smem, stream>>>(a);
     return cudaGetLastError();
 }
 
@@ -864,11 +973,13 @@ struct Launcher {
     const EvalArgs &a;
     int K, grid_x;
     cudaStream_t stream;
+    bool sweep() const { return K >= 2 && !a.emit; }
     template <int G, int R, bool DIM3, int MINB, int BUILD, int ELIM = kElim>
     cudaError_t run() const { return launch_one<T, G, R, KERN, DIM3, MINB, BUILD, ELIM>(a, K, grid_x, stream); }
 };
 template <typename T, int KERN>
 struct Describer {
+    bool sweep() const { return false; }  // grid sizing follows the single-vector kernel (same shape, same registers)
     template <int G, int R, bool DIM3, int MINB, int BUILD, int ELIM = kElim>
     ShapeInfo run() const { return ShapeInfo{blocks_per_sm<T, G, R, KERN, DIM3, MINB, BUILD, ELIM>(), 32 / G}; }
 };
@@ -886,6 +997,8 @@ auto dispatch_shape(int m, const F &f)
     }
 #endif
     if (m <= 7) return f.template run<4, 2, DIM3, 4, 0>();
+    if constexpr (F64)
+        if (m <= 15 && f.sweep()) return f.template run<4, 4, DIM3, 2, 6>();  // K >= 2: distances shared by the vectors
     if (m <= 15) return f.template run<4, 4, DIM3, (F64 ? 2 : 4), (F64 ? 2 : 0)>();
     if (m <= 31) return f.template run<8, 4, DIM3, (F64 ? 2 : 4), (F64 && DIM3 ? 0 : 1)>();
     return f.template run<16, 3, DIM3, (F64 ? 2 : 4), 1>();

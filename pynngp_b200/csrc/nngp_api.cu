@@ -398,7 +398,7 @@ int nngp_loglik_device(nngp_handle *h, int kernel_id, const double *d_params, in
     a.pts = h->pts; a.eps2 = h->eps2; a.nbr = h->nbr;
     a.lo = h->lo; a.hi = h->hi; a.m = h->m;
     a.params = d_params; a.partials = h->d_partials; a.counters = h->d_counters; a.out = d_out;
-    a.emit = 0; a.exp2tab = h->d_exp2tab;
+    a.emit = 0; a.exp2tab = h->d_exp2tab; a.K = K;
     CUDA_TRY(h, family_launch(h->dtype, kernel_id, h->m, h->D, a, K, grid, st));
     ++h->launches;
     return NNGP_OK;
@@ -478,7 +478,7 @@ int nngp_loglik_device_allreduce(nngp_handle *h, int kernel_id, const double *d_
     a.pts = h->pts; a.eps2 = h->eps2; a.nbr = h->nbr;
     a.lo = h->lo; a.hi = h->hi; a.m = h->m;
     a.params = d_params; a.partials = h->d_partials; a.counters = h->d_counters; a.out = d_out;
-    a.emit = 0; a.exp2tab = h->d_exp2tab;
+    a.emit = 0; a.exp2tab = h->d_exp2tab; a.K = K;
     a.px = px;
     CUDA_TRY(h, family_launch(h->dtype, kernel_id, h->m, h->D, a, K, grid, st));
     ++h->launches;
@@ -548,7 +548,7 @@ static int run_emit(nngp_handle *h, int kernel_id, const double *params, int64_t
         a.pts = h->pts; a.eps2 = h->eps2; a.nbr = h->nbr;
         a.lo = s0; a.hi = s1; a.m = m;
         a.params = h->d_params; a.partials = h->d_partials; a.counters = h->d_counters; a.out = h->d_out;
-        a.emit = 1; a.exp2tab = h->d_exp2tab; a.B = dB; a.F = dF; a.CN = dCN; a.cc = dcc; a.cs = dcs;
+        a.emit = 1; a.exp2tab = h->d_exp2tab; a.K = 1; a.B = dB; a.F = dF; a.CN = dCN; a.cc = dcc; a.cs = dcs;
         if (dCN) EMIT_TRY(cudaMemsetAsync(dCN, 0, sizeof(double) * cnt * m * m, h->stream));
         if (dcc) EMIT_TRY(cudaMemsetAsync(dcc, 0, sizeof(double) * cnt * m, h->stream));
         EMIT_TRY(family_launch(h->dtype, kernel_id, m, h->D, a, 1, grid_for(h, kernel_id, cnt), h->stream));

@@ -78,7 +78,8 @@ struct EvalArgs {
     const int32_t *nbr;   // n x m
     int64_t lo, hi;       // rows to evaluate
     int m;
-    const double *params;     // gridDim.y x 4 (device)
+    const double *params;     // K x 4 (device)
+    int K;                    // parameter vectors of this launch
     const double *exp2tab;    // 2^(j/2048), j < 2048
     double *partials;         // gridDim.y x gridDim.x x 3
     unsigned int *counters;   // gridDim.y

@@ -249,18 +249,51 @@ def test_loglik_fp32(n, D, m, kernel):
 
 
 def test_batched_params_and_determinism():
+    """K parameter vectors in one call: the sweep variant (pair distances computed once per location,
+    sigma2 factored out) against one-at-a-time evaluation and the oracle; odd K exercises a ragged chunk."""
     s, y = synthetic(5000, 2, 8)
     nbr = orc.c_knn_ordered(s, 15, threads=4)
+    eps2 = np.linspace(0.0, 0.05, 5000)
+    for kid, m_use in ((1, 15), (0, 9), (2, 12)):
+        e = engine(s, y, eps2)
+        e.set_neighbors(np.ascontiguousarray(np.where(np.arange(15)[None, :] < m_use, nbr, -1)[:, :m_use]))
+        tab = e.get_neighbors()
+        rng = np.random.default_rng(kid)
+        K = 11
+        prm = np.stack([rng.uniform(0.5, 2, K), rng.uniform(3, 30, K), rng.uniform(0.01, 0.5, K), np.zeros(K)], 1)
+        st = e.loglik(kid, prm)
+        assert np.array_equal(st, e.loglik(kid, prm))  # same launch shape -> bitwise identical
+        for k in range(K):
+            one = e.loglik(kid, prm[k])[0]
+            np.testing.assert_allclose(st[k, :2], one[:2], rtol=1e-11)
+            assert st[k, 2] == one[2] == 0
+        for k in (0, 5, 10):
+            st0 = orc.c_loglik(s, y, tab, kid, *prm[k, :3], eps2=eps2)
+            np.testing.assert_allclose(st[k, :2], st0[:2], rtol=RTOL64)
+    # shards and an empty shard through the batched path
+    e.set_shard(1000, 3000)
+    a = e.loglik(2, prm[:3])
+    for k in range(3):
+        st0 = orc.c_loglik(s, y, tab, 2, *prm[k, :3], eps2=eps2, lo=1000, hi=3000)
+        np.testing.assert_allclose(a[k, :2], st0[:2], rtol=RTOL64)
+    e.set_shard(7, 7)
+    assert np.array_equal(e.loglik(2, prm[:3]), np.zeros((3, 3)))
+
+
+def test_batched_non_spd_counted():
+    s = np.array([[0.0, 0.0]] * 3 + [[1.0, 1.0], [0.5, 0.5]] + [[0.1 * k, 0.3] for k in range(1, 8)])
+    y = np.ones(len(s))
     e = engine(s, y)
-    e.set_neighbors(nbr)
-    rng = np.random.default_rng(0)
-    prm = np.stack([rng.uniform(0.5, 2, 6), rng.uniform(3, 30, 6), rng.uniform(0.01, 0.5, 6), np.zeros(6)], 1)
-    st = e.loglik(1, prm)
-    for k in range(6):
-        one = e.loglik(1, prm[k])[0]
-        assert np.array_equal(one, st[k])  # same grid -> bitwise identical
-        st0 = orc.c_loglik(s, y, nbr, 1, *prm[k, :3])
-        np.testing.assert_allclose(st[k, :2], st0[:2], rtol=RTOL64)
+    e.build_neighbors(8)
+    prm = np.array([[1.0, 1.0, 0.0, 0.0], [2.0, 3.0, 0.1, 0.0]])
+    st = e.loglik(0, prm)
+    # vector 0: coincident sites without a nugget are exactly singular -- the locations are counted and
+    # left out, never a NaN (which of the knife-edge pivots round to <= 0 is arithmetic-dependent, so the
+    # count itself is not compared); vector 1 has a nugget: regular, must match the oracle
+    assert st[0, 2] >= 1 and np.isfinite(st).all()
+    st1 = orc.c_loglik(s, y, e.get_neighbors(), 0, *prm[1, :3])
+    assert st[1, 2] == 0 and st1[2] == 0
+    np.testing.assert_allclose(st[1, :2], st1[:2], rtol=RTOL64)
 
 
 def test_shards_sum_to_whole_and_empty_shard():
