@@ -673,8 +673,9 @@ __global__ void __launch_bounds__(kThreads, MINB) fused_loglik_kernel(const Eval
 
         // sweep: one pass of [covariances from the stored distances -> elimination -> accumulation] per
         // parameter vector of the chunk; otherwise a single pass over the matrix built above
+        int kk = 0;
 #pragma unroll 1
-        for (int kk = 0; kk < (SWEEP ? kc : 1); ++kk) {
+        do {
         volatile double *ab = accbuf + (SWEEP ? kk * 128 : 0);
         if constexpr (SWEEP) {
             constexpr int CBs = 6;
@@ -847,7 +848,7 @@ __global__ void __launch_bounds__(kThreads, MINB) fused_loglik_kernel(const Eval
             }
         }
         if constexpr (SWEEP) __syncwarp();  // the column buffers are rewritten by the next parameter vector
-        }  // parameter vectors
+        } while (SWEEP && ++kk < kc);  // parameter vectors (a single pass outside the sweep variant)
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");  // drain copies issued for groups past the end
 
