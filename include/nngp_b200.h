@@ -126,7 +126,7 @@ int nngp_loglik_device(nngp_handle *h, int kernel_id, const double *d_params, in
  * ALL ranks, bitwise identical on every rank: the last block of each rank stores its K x 3 partials into
  * every peer's buffer over NVLink (P2P stores), flags them, waits for all ranks' flags and sums in rank
  * order -- no second launch, no NCCL call.  Every rank must issue the same sequence of these calls.  If a
- * peer does not arrive within ~2 s the statistics come back as NaN. */
+ * peer does not arrive within ~30 s the statistics come back as NaN. */
 #define NNGP_IPC_HANDLE_BYTES 64
 int nngp_peer_export(nngp_handle *h, int K_cap, unsigned char *handle_out);
 int nngp_peer_connect(nngp_handle *h, int rank, int world, const unsigned char *handles);

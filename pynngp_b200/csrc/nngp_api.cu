@@ -75,14 +75,19 @@ cudaError_t family_launch(int dtype, int kernel_id, int m, int D, const EvalArgs
     return nngp_launch_f32_m52(m, D, a, K, grid_x, stream);
 }
 
-// grid.x for nloc locations: enough resident blocks to fill every SM, never more than the work
+// grid.x for nloc locations: enough resident blocks to fill every SM, never more than the work.  The
+// occupancy query is cached per (kernel family, m, D): it costs several microseconds of host time.
 int grid_for(nngp_handle *h, int kernel_id, int64_t nloc)
 {
-    int per_sm = 1, lpw = 8;
-    family_shape(h->dtype, kernel_id, h->m, h->D, &per_sm, &lpw);
-    const int64_t groups = (nloc + lpw - 1) / lpw;
+    const int key = ((kernel_id * 64 + h->m) * 4 + h->D) * 2 + h->dtype;
+    if (h->shape_key != key) {
+        int per_sm = 1, lpw = 8;
+        family_shape(h->dtype, kernel_id, h->m, h->D, &per_sm, &lpw);
+        h->shape_key = key; h->shape_per_sm = per_sm; h->shape_lpw = lpw;
+    }
+    const int64_t groups = (nloc + h->shape_lpw - 1) / h->shape_lpw;
     const int64_t need = (groups + 3) / 4;  // 4 warps per block
-    int64_t g = int64_t(h->num_sms) * per_sm;
+    int64_t g = int64_t(h->num_sms) * h->shape_per_sm;
     if (g > need) g = need;
     if (g < 1) g = 1;
     return int(g);

@@ -67,6 +67,8 @@ struct nngp_handle {
     void *peer_base[NNGP_MAX_PEERS] = {};
     PeerExchange px;
 
+    int shape_key = -1, shape_per_sm = 1, shape_lpw = 8;  // cached occupancy of the fused kernel in use
+
     int64_t launches = 0;
     std::string err;
 };

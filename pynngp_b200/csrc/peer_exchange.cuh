@@ -12,7 +12,7 @@
 
 // Called by all threads of the (single) block that holds the rank's totals for parameter vector k; needs
 // blockDim.x >= px.world.  v0..v2 are read from thread 0.  Returns the all-rank sums to thread 0 through
-// out3 (NaN after a 2 s timeout: a peer never arrived).
+// out3 (NaN after a ~30 s timeout: a peer never arrived).
 __device__ __forceinline__ void peer_allreduce3(const PeerExchange &px, int k, double v0, double v1, double v2,
                                                 double *sh /* >= 3 + 8 doubles of shared memory */, double out3[3])
 {
@@ -32,7 +32,7 @@ __device__ __forceinline__ void peer_allreduce3(const PeerExchange &px, int k, d
         const long long t0 = clock64();
         bool ok = true;
         while (*mf != px.gen) {
-            if (clock64() - t0 > 4000000000ll) { ok = false; break; }
+            if (clock64() - t0 > 60000000000ll) { ok = false; break; }  // ~30 s: ranks may be launched seconds apart
             __nanosleep(64);
         }
         __threadfence_system();

@@ -295,6 +295,8 @@ class NNGP(object):
             for c in range(self._y2d.shape[1]):
                 self._set_column(c)
                 total += self._engine.loglik_allreduce(self._kernel.kernel_id, params)
+            if np.isnan(total).any():
+                raise RuntimeError("the cross-GPU exchange timed out: a rank never launched its evaluation")
             return total
         import torch
 
