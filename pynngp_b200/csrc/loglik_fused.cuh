@@ -997,9 +997,11 @@ auto dispatch_shape(int m, const F &f)
         if (!strcmp(e, "m2cb12")) return f.template run<4, 4, DIM3, 2, 4>();    // 12-pair batches
     }
 #endif
+    if constexpr (F64) {  // K >= 2: the sweep variant (distances shared by the parameter vectors)
+        if (m <= 7 && f.sweep()) return f.template run<4, 2, DIM3, 4, 6>();
+        if (m <= 15 && f.sweep()) return f.template run<4, 4, DIM3, 2, 6>();
+    }
     if (m <= 7) return f.template run<4, 2, DIM3, 4, 0>();
-    if constexpr (F64)
-        if (m <= 15 && f.sweep()) return f.template run<4, 4, DIM3, 2, 6>();  // K >= 2: distances shared by the vectors
     if (m <= 15) return f.template run<4, 4, DIM3, (F64 ? 2 : 4), (F64 ? 2 : 0)>();
     if (m <= 31) return f.template run<8, 4, DIM3, (F64 ? 2 : 4), (F64 && DIM3 ? 0 : 1)>();
     return f.template run<16, 3, DIM3, (F64 ? 2 : 4), 1>();

@@ -254,7 +254,7 @@ def test_batched_params_and_determinism():
     s, y = synthetic(5000, 2, 8)
     nbr = orc.c_knn_ordered(s, 15, threads=4)
     eps2 = np.linspace(0.0, 0.05, 5000)
-    for kid, m_use in ((1, 15), (0, 9), (2, 12)):
+    for kid, m_use in ((1, 15), (0, 9), (2, 12), (1, 5)):
         e = engine(s, y, eps2)
         e.set_neighbors(np.ascontiguousarray(np.where(np.arange(15)[None, :] < m_use, nbr, -1)[:, :m_use]))
         tab = e.get_neighbors()
