@@ -170,3 +170,56 @@ def test_krige_known_answers():
         assert sorted(tab[0].tolist()) == list(range(40))
     mean, var, _ = orc.np_krige(s, y, np.array([[500.0, 500.0]]), 6, 0, 1.2, 4.0, 0.05)
     assert abs(mean[0]) < 1e-200 and var[0] == 1.25
+
+
+# ---- the cell-grid search's algorithm (CPU model of knn_grid.cu): stopping never changes the result ----
+def _grid_cases():
+    rng = np.random.default_rng(42)
+    lattice = np.stack(np.meshgrid(np.arange(24.0), np.arange(20.0)), -1).reshape(-1, 2)
+    yield "uniform2d", rng.random((900, 2)), 15
+    yield "uniform3d", rng.random((700, 3)), 30
+    yield "uniform1d", rng.random((600, 1)), 7
+    yield "lattice_ties", lattice[rng.permutation(len(lattice))] / 7.0, 8
+    yield "duplicates", np.repeat(rng.random((60, 2)), 8, axis=0)[rng.permutation(480)], 12
+    yield "all_same", np.full((300, 3), 0.25), 5
+    yield "collapsed_dim", np.stack([rng.random(500), np.full(500, 2.0)], 1), 9
+    yield "thin_dim", np.stack([rng.random(600), 1e-7 * rng.random(600), rng.random(600)], 1), 10
+    yield "huge_offset", rng.random((500, 2)) * 1e-3 + 1e6, 10
+    yield "negative_box", rng.random((500, 3)) * [5.0, 0.01, 300.0] - [2.5, 1e3, 150.0], 6
+    yield "clusters", np.concatenate([0.5 + 0.01 * rng.standard_normal((400, 2)), rng.random((150, 2)),
+                                      0.2 + 1e-4 * rng.standard_normal((150, 2))])[rng.permutation(700)], 15
+    yield "m32", rng.random((400, 2)), 32
+    yield "m1", rng.random((400, 3)), 1
+
+
+@pytest.mark.parametrize("name,s,m", list(_grid_cases()), ids=[c[0] for c in _grid_cases()])
+def test_grid_search_model_is_exact(name, s, m):
+    from oracle import grid_knn_model as gm
+
+    want = orc.c_knn_ordered(s, m)
+    for lam in (0.15, 1.0, 5.0):
+        st = {}
+        got = gm.grid_knn_ordered(s, m, lam_scale=lam, brute_rows=128, stats=st)
+        assert np.array_equal(got, want), (name, lam)
+    # and the walk really prunes on well-spread data: far fewer candidates than the n^2/2 of brute force
+    if name == "uniform2d":
+        st = {}
+        gm.grid_knn_ordered(s, m, 1.0, 128, stats=st)
+        assert st["candidates"] < 0.5 * len(s) * len(s) / 2
+
+
+def test_grid_search_model_random_sweep():
+    """Seeded sweep over sizes, dimensions, m, cell sizes, anisotropic boxes and offsets."""
+    from oracle import grid_knn_model as gm
+
+    rng = np.random.default_rng(7)
+    for _ in range(30):
+        D = int(rng.integers(1, 4))
+        n = int(rng.integers(200, 1200))
+        m = int(rng.integers(1, 33))
+        s = rng.random((n, D)) * rng.choice([1e-3, 1.0, 40.0], D) + rng.choice([0.0, -7.0, 1e5], D)
+        if rng.random() < 0.3:  # coarse coordinates: many exact ties
+            s = np.round(s, 2)
+        want = orc.c_knn_ordered(s, m)
+        got = gm.grid_knn_ordered(s, m, lam_scale=float(rng.choice([0.2, 1.0, 3.0])), brute_rows=128)
+        assert np.array_equal(got, want), (D, n, m)
