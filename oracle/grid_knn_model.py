@@ -91,7 +91,7 @@ def grid_knn_ordered(s, m, lam_scale=1.0, brute_rows=128, stats=None):
     a = T0
     while a < n:
         b = min(2 * a, n)
-        gs = make_grid(bb_lo, bb_hi, D, float(a), lam, max(2 * n, 1024))
+        gs = make_grid(bb_lo, bb_hi, D, float(a), lam, max(8 * n, 1024))
         G = gs["G"]
         cc = cell_coords(gs, pts[:b])
         cid = (cc[:, 2] * G[1] + cc[:, 1]) * G[0] + cc[:, 0]

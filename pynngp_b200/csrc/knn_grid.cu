@@ -380,7 +380,7 @@ cudaError_t launch_knn_grid(nngp_handle *h, bool ordered, int m, int64_t row_lo,
                                      (h->D > 2 && h->bb_hi[2] > h->bb_lo[2]));
     const double ball = deff == 1 ? 2.0 : deff == 2 ? 3.141592653589793 : 4.1887902047863905;
     const double lambda = std::max(1.0, h->knn_lambda_scale * (m + 2.0 * sqrt(double(m))) / ball);
-    const int64_t max_cells = std::min<int64_t>(std::max<int64_t>(2 * n, 1024), int64_t(1) << 30);
+    const int64_t max_cells = std::min<int64_t>(std::max<int64_t>(8 * n, 1024), int64_t(1) << 28);  // reached only by refinement
 
     // levels, top (largest) first; the top level's histogram decides whether a grid pays off
     struct Level { int64_t a, b; };
@@ -396,14 +396,29 @@ cudaError_t launch_knn_grid(nngp_handle *h, bool ordered, int m, int64_t row_lo,
         lev[nlev++] = Level{0, n};
     }
 
-    Scratch sc;
     bool any_level = false;
     for (int l = nlev - 1; l >= 0; --l)
         if (std::max(lev[l].a, row_lo) < std::min(lev[l].b, row_hi)) any_level = true;
+
+    const bool dim3 = h->D == 3;
+    auto qkern = ordered ? (dim3 ? knn_grid_query_kernel<true, true> : knn_grid_query_kernel<false, true>)
+                         : (dim3 ? knn_grid_query_kernel<true, false> : knn_grid_query_kernel<false, false>);
+    const size_t smem = query_smem(m);
+    GRID_TRY(cudaFuncSetAttribute(qkern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const bool partial = row_lo > 0 || row_hi < n;
+    bool filled = false;
+
+    // Clustered data: when the top level's histogram predicts too much work, the cells are refined (a
+    // quarter of the occupancy per attempt: dense regions get small cells, sparse regions cost a few more
+    // rings of mostly empty cells) before brute force is considered.
+    double lam_use = lambda;
+    for (int attempt = 0;; ++attempt) {
+    Scratch sc;
+    bool rejected = false;
     int cap_cells = 0;
     if (any_level) {
         for (int l = 0; l < nlev; ++l)
-            cap_cells = std::max(cap_cells, make_grid(h, double(ordered ? std::min(lev[l].a, cand_cap) : n), lambda, max_cells).ncell);
+            cap_cells = std::max(cap_cells, make_grid(h, double(ordered ? std::min(lev[l].a, cand_cap) : n), lam_use, max_cells).ncell);
         GRID_TRY(cudaMalloc(&sc.sorted, sizeof(double4) * size_t(n)));
         GRID_TRY(cudaMalloc(&sc.cell_of, sizeof(int) * size_t(n)));
         GRID_TRY(cudaMalloc(&sc.qlist, sizeof(int) * size_t(n)));
@@ -413,21 +428,13 @@ cudaError_t launch_knn_grid(nngp_handle *h, bool ordered, int m, int64_t row_lo,
     int *counts = sc.cells, *starts = counts + (cap_cells + 1), *cursor = starts + (cap_cells + 1);
     int *qcounts = cursor + (cap_cells + 1), *qstarts = qcounts + (cap_cells + 1), *qcursor = qstarts + (cap_cells + 1);
 
-    const bool dim3 = h->D == 3;
-    auto qkern = ordered ? (dim3 ? knn_grid_query_kernel<true, true> : knn_grid_query_kernel<false, true>)
-                         : (dim3 ? knn_grid_query_kernel<true, false> : knn_grid_query_kernel<false, false>);
-    const size_t smem = query_smem(m);
-    GRID_TRY(cudaFuncSetAttribute(qkern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-
-    const bool partial = row_lo > 0 || row_hi < n;
-    bool filled = false;
     bool first = true;
     for (int l = nlev - 1; l >= 0; --l) {
         const int64_t qlo = std::max(lev[l].a, row_lo), qhi = std::min(lev[l].b, row_hi);
         if (qlo >= qhi) continue;
         const int N = int(lev[l].b);
         const int ncand = int(std::min<int64_t>(N, cand_cap));
-        const GridSpec gs = make_grid(h, double(ordered ? std::min(lev[l].a, cand_cap) : n), lambda, max_cells);
+        const GridSpec gs = make_grid(h, double(ordered ? std::min(lev[l].a, cand_cap) : n), lam_use, max_cells);
         GRID_TRY(cudaMemsetAsync(counts, 0, sizeof(int) * size_t(gs.ncell + 1), stream));
         GRID_TRY(cudaMemsetAsync(qcounts, 0, sizeof(int) * size_t(gs.ncell + 1), stream));
         const int sgrid = int(std::min<int64_t>((N + 255) / 256, int64_t(h->num_sms) * 16));
@@ -447,7 +454,7 @@ cudaError_t launch_knn_grid(nngp_handle *h, bool ordered, int m, int64_t row_lo,
                 GRID_TRY(cudaMemcpyAsync(&sumsq, sc.sumsq, sizeof(double), cudaMemcpyDeviceToHost, stream));
                 GRID_TRY(cudaStreamSynchronize(stream));
                 const double est = pow(3.0, deff) * sumsq;
-                if (est > double(ncand) * double(ncand) / 16.0) return cudaSuccess;  // *used stays 0
+                if (est > double(ncand) * double(ncand) / 16.0) { rejected = true; break; }  // nothing written yet
             }
         }
         if (partial && !filled) {
@@ -465,6 +472,10 @@ cudaError_t launch_knn_grid(nngp_handle *h, bool ordered, int m, int64_t row_lo,
         GRID_TRY(cudaGetLastError());
         h->launches += 2;
     }
+    if (!rejected) break;
+    if (attempt == 4 || int64_t(cap_cells) * 2 > max_cells) return cudaSuccess;  // *used stays 0: brute force
+    lam_use *= 0.25;
+    }  // attempts
     if (partial && !filled) {
         fill_rows_kernel<<<h->num_sms * 4, 256, 0, stream>>>(table, n * int64_t(m), NNGP_ROW_UNSET);
         GRID_TRY(cudaGetLastError());

@@ -133,6 +133,15 @@ def test_knn_grid_matches_oracle_mid_size(n, D, m):
 
 def test_knn_grid_clustered_and_auto():
     rng = np.random.default_rng(11)
+    # one dense blob over a uniform background: the default cells are rejected by the work estimate, the
+    # refined ones (a quarter of the occupancy per attempt) are accepted
+    mod = np.concatenate([0.5 + 0.01 * rng.standard_normal((18000, 2)), rng.random((12000, 2))])
+    mod = mod[rng.permutation(len(mod))]
+    want = orc.c_knn_ordered(mod, 15, threads=os.cpu_count() or 1)
+    e, got = grid_table(mod, 15, 1.0, 8192, algo="auto")
+    assert e.knn_used_grid() and np.array_equal(got, want)
+    # blobs whose densities differ by three orders of magnitude defeat any single cell size: auto may fall
+    # back to brute force, a forced grid is slow there -- the table is the same either way
     blobs = np.concatenate([0.5 + 0.01 * rng.standard_normal((15000, 2)), rng.random((5000, 2)),
                             0.2 + 0.0005 * rng.standard_normal((5000, 2))])
     s = blobs[rng.permutation(len(blobs))]

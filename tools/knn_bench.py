@@ -48,3 +48,18 @@ for rows in [int(r) for r in a.rows.split(",")]:
         elif not a.brute:
             ok = "  == first" if np.array_equal(tab, ref) else "  MISMATCH vs first"
         print(f"grid lam={lam} brute_rows={rows}: {best:.4f}s{ok}", flush=True)
+if os.environ.get("KNN_CLUSTERED"):
+    # clustered sites: Gaussian blobs of very different scales over a uniform background
+    rng = np.random.default_rng(1)
+    k = n // 4
+    sc = np.concatenate([0.5 + 0.01 * rng.standard_normal((2 * k, c["D"])), rng.random((k, c["D"])),
+                         0.2 + 0.0005 * rng.standard_normal((n - 3 * k, c["D"]))])[rng.permutation(n)]
+    e.set_data(sc, y)
+    e.set_knn_tuning(1.0, 4096)
+    for algo in ("auto", "brute"):
+        t0 = time.perf_counter()
+        e.build_neighbors_grid(c["m"], 0, None, algo)
+        dt = time.perf_counter() - t0
+        tab = e.get_neighbors()
+        print(f"clustered {algo}: {dt:.4f}s used_grid={e.knn_used_grid()}" + ("" if algo == "auto" else f"  equal={np.array_equal(tab, prev)}"), flush=True)
+        prev = tab
