@@ -11,6 +11,16 @@ What is kept from the reference (drop-in contract):
     ``NotImplementedError`` here.
 What is added: ``loglik``, ``loglik_terms``, ``loglik_batch``, ``factors`` and keyword-only engine
 options.  There is no CPU fallback: constructing an ``NNGP`` without a B200 raises.
+
+Reference sets other than T (nngp.py:32-40, 68-71).  ``refType = ('subset', nRef)`` and
+``('random', nRef, bounds)`` crash upstream (``self.typ`` is never set, nngp.py:34); here they build what
+the reference's code intends: ``s``, ``ws`` (5-NN regression of (t, y) evaluated at s), ``Ns`` (ordered
+neighbours within s) and ``Nt`` (for every t_i the pair ``KDTree(s).query(t_i, m)`` returns: distances and
+indices of its m nearest reference sites).  The engine then holds the rows [s ; T - S]: the first nRef
+rows condition on their predecessors in s, every remaining observation on its m nearest reference sites --
+the NNGP density of Datta et al. (2016) for S a subset of T -- so ``loglik`` stays one launch of the same
+fused kernel.  For 'random' no response is observed at s: the neighbour structure and the per-location
+accessors exist, ``loglik`` raises.
 """
 from __future__ import annotations
 
@@ -46,9 +56,39 @@ class NeighborSets:
         return (self[i] for i in range(len(self)))
 
 
+def _dist_rows(a, b):
+    """Euclidean distances from the point a (D,) to the rows of b (k, D), accumulated dimension by
+    dimension as scikit-learn's KDTree does (sklearn/metrics/_dist_metrics.pxd.tp:39-49)."""
+    d2 = np.zeros(len(b))
+    for k in range(b.shape[1]):
+        t = a[k] - b[:, k]
+        d2 = d2 + t * t
+    return np.sqrt(d2)
+
+
+class QueryNeighborSets:
+    """``Nt`` for S != T (nngp.py:68-71): ``Nt[i]`` is what ``KDTree(s).query(t_i.reshape(1, -1), m)``
+    returns -- the pair (distances (1, m) float64, indices into s (1, m) int64), nearest first."""
+
+    def __init__(self, table, t, s):
+        self.table, self._t, self._s = table, t, s
+
+    def __len__(self):
+        return self.table.shape[0]
+
+    def __getitem__(self, i):
+        if isinstance(i, slice):
+            return [self[k] for k in range(*i.indices(len(self)))]
+        idx = self.table[i].astype(np.int64)
+        return _dist_rows(self._t[i], self._s[idx])[None, :], idx[None, :]
+
+    def __iter__(self):
+        return (self[i] for i in range(len(self)))
+
+
 class NNGP(object):
     def __init__(self, t, y, eps, refType, m, cov, *, dtype="float64", device=None, neighbors=None,
-                 group=None, knn="auto"):
+                 group=None, knn="auto", seed=None):
         self.t = t  # ordinates
         self.y = y  # abscissae
         self.eps = eps  # measurement uncertainties in y
@@ -67,6 +107,7 @@ class NNGP(object):
         self._engine = _lib.Engine(device=device, dtype=dtype)
         self._ycol = None
         self._timings = {}
+        self._seed = seed  # S != T only: None = numpy's global RNG as in the reference (nngp.py:36, 40)
 
         self._init_s()
         self._init_wt()
@@ -118,28 +159,79 @@ class NNGP(object):
         return int(flag.item()) == 1
 
     def _init_s(self):
-        # nngp.py:21-40.  Only 'S=T' works upstream (the tuple branches read an unset attribute,
-        # nngp.py:34); they change the model to a latent NNGP and are out of the likelihood path.
-        if isinstance(self.refType, str) and self.refType == "S=T":
+        # nngp.py:21-40.  Upstream only 'S=T' runs: the tuple branches read `self.typ`, which is never
+        # set (nngp.py:34).  They are built here as written otherwise, with two repairs: the subset is
+        # drawn without replacement (a repeated reference site makes C_N singular) and the draw can be
+        # seeded (`seed=`; required with several ranks, which must all hold the same s).
+        rt = self.refType
+        self._choice = None
+        if isinstance(rt, str):
+            if rt != "S=T":
+                raise ValueError("refType must be 'S=T', ('subset', nRef) or ('random', nRef, bounds)")
+            self._ref_kind = "S=T"
             self.s = self.t
+            return
+        if not (isinstance(rt, tuple) and rt and rt[0] in ("subset", "random")):
+            raise ValueError("refType must be 'S=T', ('subset', nRef) or ('random', nRef, bounds)")
+        if self._seed is None and self._world > 1:
+            raise ValueError("refType %r needs seed= when several ranks must draw the same reference set" % (rt[0],))
+        rng = np.random if self._seed is None else np.random.default_rng(self._seed)
+        typ, nRef = rt[0], int(rt[1])
+        t = np.asarray(self.t)
+        if nRef < 1:
+            raise ValueError("nRef must be >= 1")
+        if typ == "subset":
+            if nRef > len(t):
+                raise ValueError("a subset of T cannot hold more than len(t) sites")
+            self._choice = np.asarray(rng.choice(len(t), size=nRef, replace=False), dtype=np.int64)
+            self.s = t[self._choice]
         else:
-            raise NotImplementedError("only refType='S=T' is supported (the reference's other branches crash)")
+            bounds = rt[2]
+            if len(bounds) != (1 if t.ndim == 1 else t.shape[1]):
+                raise ValueError("bounds needs one (lo, hi) pair per dimension of t")
+            self.s = np.vstack([rng.uniform(lo, hi, nRef) for lo, hi in bounds]).T
+        self._ref_kind = typ
+        if self.m > nRef:
+            # what KDTree(s).query(t_i, m) raises upstream (nngp.py:70-71)
+            raise ValueError("m must be less than or equal to the number of reference sites")
 
     def _init_wt(self):
         self.wt = np.copy(self.y)  # nngp.py:42-43
 
     def _upload(self):
-        s = np.ascontiguousarray(self.s, dtype=np.float64)
-        if s.ndim == 1:
-            s = s[:, None]
+        """Engine row layout.  S = T: the rows of t.  'subset': [s ; T - S] (T - S in the order of t) with
+        y and eps permuted alike.  'random': the rows of s only (no response is observed there)."""
+        def as2d(a):
+            a = np.ascontiguousarray(a, dtype=np.float64)
+            return a[:, None] if a.ndim == 1 else a
+
+        s = as2d(self.s)
         if not np.isfinite(s).all():
             raise ValueError("coordinates must be finite")
-        n = s.shape[0]
+        self._n_ref = len(s)
         y = np.asarray(self.y, dtype=np.float64)
-        self._y2d = y.reshape(n, -1)
-        eps = np.broadcast_to(np.asarray(self.eps, dtype=np.float64).reshape((n, -1) if np.ndim(self.eps) else (1, 1)),
-                              self._y2d.shape)
-        self._eps2 = None if not np.any(eps) else np.ascontiguousarray(eps * eps)
+        nt = len(np.asarray(self.t))
+        y2d = y.reshape(nt, -1)
+        eps = np.broadcast_to(np.asarray(self.eps, dtype=np.float64).reshape((nt, -1) if np.ndim(self.eps) else (1, 1)),
+                              y2d.shape)
+        eps2 = None if not np.any(eps) else np.ascontiguousarray(eps * eps)
+        self._yt2d = y2d  # the response in the order of t (what `ws` averages)
+        self._rows = None  # engine row -> row of t
+        if self._ref_kind == "subset":
+            t = as2d(self.t)
+            if not np.isfinite(t).all():
+                raise ValueError("coordinates must be finite")
+            rest = np.setdiff1d(np.arange(nt), self._choice)
+            self._rows = np.concatenate([self._choice, rest])
+            s = np.ascontiguousarray(t[self._rows])
+            y2d = np.ascontiguousarray(y2d[self._rows])
+            eps2 = None if eps2 is None else np.ascontiguousarray(eps2[self._rows])
+        elif self._ref_kind == "random":
+            y2d = np.zeros((len(s), y2d.shape[1]))
+            eps2 = None
+        n = len(s)
+        self._y2d = y2d
+        self._eps2 = eps2
         self._coords = s
         import time
 
@@ -175,6 +267,17 @@ class NNGP(object):
             neighbors = np.load(neighbors)  # a table written by save_neighbors()
         if neighbors is not None:
             eng.set_neighbors(neighbors)
+        elif self._ref_kind != "S=T":
+            # nngp.py:49-62 on s (rows [0, nRef): ordered search among predecessors) and nngp.py:68-71
+            # for the rows of T - S (their m nearest reference sites, any index); every rank builds the
+            # whole table
+            eng.build_neighbors_grid(self.m, 0, self._n_ref, self._knn)
+            table = eng.get_neighbor_rows(0, self._n_ref)
+            if eng.n > self._n_ref:
+                table = np.concatenate([table, self._nt_table[self._rows[self._n_ref:]]])
+            eng.set_neighbors(table)
+            eng.set_shard(*self._shard)
+            neighbors = table
         elif self._world == 1:
             eng.build_neighbors_grid(self.m, 0, eng.n, self._knn)
         else:
@@ -208,15 +311,46 @@ class NNGP(object):
     def Ns(self):
         """The reference's list of neighbour index arrays (nngp.py:49-62)."""
         if self._Ns is None:
-            self._Ns = NeighborSets(self._table)
+            self._Ns = NeighborSets(self._table[: self._n_ref])
         return self._Ns
 
     @property
     def Nt(self):
-        return self.Ns  # nngp.py:65-67: the same object
+        if self._ref_kind == "S=T":
+            return self.Ns  # nngp.py:65-67: the same object
+        if self._Nt is None:
+            t = np.asarray(self.t, dtype=np.float64)
+            self._Nt = QueryNeighborSets(self._nt_table, t[:, None] if t.ndim == 1 else t, self._coords_s())
+        return self._Nt
 
     def _make_t_neighbor_sets(self):
-        pass  # nngp.py:65-67 for S = T: Nt is Ns (see the property above)
+        # nngp.py:65-71.  S = T: Nt is Ns.  Otherwise the (len(t), m) table of nearest reference sites is
+        # searched on the GPU the first time it is needed (see _nt_table) and wrapped by the Nt property.
+        self._Nt = None
+
+    def _coords_s(self):
+        return self._coords[: self._n_ref]
+
+    def _nearest_rows(self, ref, queries, k):
+        """(len(queries), k) int32: the k nearest rows of `ref` for every query row, ascending (d2, j) --
+        the capped search of the hot path (queries appended after the reference rows, candidates j <
+        len(ref)), on a scratch engine."""
+        eng = _lib.Engine(device=self._engine.device, dtype=self._engine.dtype)
+        try:
+            n, q = len(ref), len(queries)
+            eng.set_data(np.concatenate([ref, queries]), np.zeros(n + q), None)
+            eng.build_neighbors_capped(k, n, n + q, n, self._knn)
+            return eng.get_neighbor_rows(n, n + q)
+        finally:
+            eng.close()
+
+    @property
+    def _nt_table(self):
+        """S != T: row i = the m nearest reference sites of t_i (nngp.py:68-71), indices into s."""
+        if getattr(self, "_nt_table_host", None) is None:
+            t = np.ascontiguousarray(self.t, dtype=np.float64)
+            self._nt_table_host = self._nearest_rows(self._coords_s(), t[:, None] if t.ndim == 1 else t, self.m)
+        return self._nt_table_host
 
     @property
     def ws(self):
@@ -224,10 +358,15 @@ class NNGP(object):
         over the 5 nearest sites of each site, itself included -- what scikit-learn's
         ``KNeighborsRegressor(5, 'uniform').fit(t, y).predict(s)`` returns for S = T.  Computed lazily
         on the GPU (plain k-NN kernel) the first time it is read; not used by the likelihood."""
-        if self._ws is None:
+        if self._ws is None and self._ref_kind == "S=T":
             k = min(5, len(self._coords))
             idx = self._engine.knn_plain(k)
             self._ws = self._y2d[idx].mean(axis=1).reshape(np.shape(self.y))
+        elif self._ws is None:
+            # S != T: the regressor is fitted on (t, y) and evaluated at s
+            t = np.ascontiguousarray(self.t, dtype=np.float64)
+            idx = self._nearest_rows(t[:, None] if t.ndim == 1 else t, self._coords_s(), min(5, len(t)))
+            self._ws = self._yt2d[idx].mean(axis=1).reshape((self._n_ref,) + np.shape(self.y)[1:])
         return self._ws
 
     # ---- parameters -------------------------------------------------------------------------------
@@ -272,6 +411,9 @@ class NNGP(object):
     def loglik_batch(self, params):
         """params (K, 3|4) rows of (sigma2, phi, tau2[, nu]) -> (K, 3) global statistics
         [sum log F, sum r^2/F, n_bad], summed over response columns and over all ranks."""
+        if self._ref_kind == "random":
+            raise NotImplementedError("refType ('random', ...) observes no response at the reference sites: the "
+                                      "response likelihood needs S = T or a subset of T")
         params = np.atleast_2d(np.asarray(params, dtype=np.float64))
         if params.shape[1] == 3:
             params = np.concatenate([params, np.zeros((params.shape[0], 1))], axis=1)
@@ -366,7 +508,9 @@ class NNGP(object):
             raise ValueError("t_new must have the reference sites' dimension")
         if not np.isfinite(tn).all():
             raise ValueError("coordinates must be finite")
-        n, q = len(self._coords), len(tn)
+        if self._ref_kind == "random":
+            raise NotImplementedError("refType ('random', ...) observes no response at the reference sites")
+        n, q = self._n_ref, len(tn)  # kriging conditions on the reference sites (the first rows of the engine)
         m = self.m if m is None else int(m)
         prm = self._params(sigma2, phi, tau2)
         ncol = self._y2d.shape[1]
@@ -375,12 +519,12 @@ class NNGP(object):
         if q == 0:
             return mean.reshape((0,) + np.shape(self.y)[1:]), var.reshape((0,) + np.shape(self.y)[1:])
         eng = _lib.Engine(device=self._engine.device, dtype=self._engine.dtype)
-        coords = np.concatenate([self._coords, tn])
+        coords = np.concatenate([self._coords[:n], tn])
         B = F = tab = None
         for c in range(ncol):
             if B is None or self._eps2 is not None:  # weights depend on the column only through eps
-                eps2 = None if self._eps2 is None else np.concatenate([self._eps2[:, c], np.zeros(q)])
-                eng.set_data(coords, np.concatenate([self._y2d[:, c], np.zeros(q)]), eps2)
+                eps2 = None if self._eps2 is None else np.concatenate([self._eps2[:n, c], np.zeros(q)])
+                eng.set_data(coords, np.concatenate([self._y2d[:n, c], np.zeros(q)]), eps2)
                 if tab is None:
                     eng.build_neighbors_capped(m, n, n + q, n, self._knn)
                     tab = eng.get_neighbor_rows(n, n + q)
