@@ -122,6 +122,26 @@ def oracle_sample_rate(s, y, m, kid, threads, sample, min_seconds):
     return per_loc * n, f"{hi - lo} contiguous rows [{lo},{hi}) x {reps} reps, scaled to n={n}"
 
 
+def reference_stage1_timing(cfg, sizes=(1000, 2000, 4000)):
+    """The reference's stage 1 as written (nngp.py:49-62: a scikit-learn KD-tree rebuilt for every i) timed
+    on this host at small n -- the only part of the path the reference implements, single-threaded by
+    construction -- with the quadratic extrapolation to the workload's n (x3.4-4.0 per
+    doubling).  A few seconds of CPU work."""
+    from oracle import nngp_oracle as orc  # the checker's restatement of the reference's own calls
+
+    s, _ = synthetic(max(sizes), cfg["D"], cfg["seed"])
+    orc.sk_reference_stage1(s[:200], cfg["m"])  # untimed: imports scikit-learn and warms its first call
+    secs = []
+    for k in sizes:
+        t0 = time.perf_counter()
+        orc.sk_reference_stage1(s[:k], cfg["m"])
+        secs.append(time.perf_counter() - t0)
+    per_pair = secs[-1] / (sizes[-1] ** 2)
+    return {"what": "pyNNGP/nngp.py:49-62 as written (KDTree(s[0:i]) per i, scikit-learn), 1 thread",
+            "n": list(sizes), "seconds": secs, "extrapolated_seconds_at_workload_n": per_pair * float(cfg["n"]) ** 2,
+            "extrapolation": "quadratic from the largest n timed"}
+
+
 def run_reference(args, cfg):
     """--impl reference: rank 0 only; other ranks exit without work."""
     if int(os.environ.get("RANK", "0")) != 0:
@@ -143,7 +163,8 @@ def run_reference(args, cfg):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": workload_config(cfg, args.gpus),
-        "cpu_baseline": {"value": value, "unit": "evals/s", "cores": threads, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "evals/s", "cores": threads, "kind": "port", "sample": sample,
+                         "stage1_reference": reference_stage1_timing(cfg)},
         "e2e": {"value": value, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "the reference (pyNNGP/nngp.py:73-96) has no likelihood implementation and no compiled sources; "
                 "this arm times the C oracle port of its stubbed path on all host threads",
@@ -357,6 +378,11 @@ def run_ours(args, cfg):
     threads = os.cpu_count() or 1
     sec_cpu, sample = oracle_sample_rate(s, y, cfg["m"], kid, threads, args.cpu_sample, 10.0)
     cpu_baseline = {"value": 1.0 / sec_cpu, "unit": "evals/s", "cores": threads, "kind": "port", "sample": sample}
+    try:
+        cpu_baseline["stage1_reference"] = reference_stage1_timing(cfg)
+        cpu_baseline["stage1_reference"]["ours_seconds_at_workload_n"] = knn_s
+    except Exception as exc:  # scikit-learn missing on the host: the likelihood baseline above still stands
+        cpu_baseline["stage1_reference"] = {"unavailable": repr(exc)}
 
     # parity spot check on the very numbers being timed (cheap: the sample's rows)
     ms_per_step = total_ms / args.steps

@@ -61,6 +61,23 @@ def np_knn_ordered(s, m):
     return Ns
 
 
+def sk_reference_stage1(s, m):
+    """The reference's stage 1 AS WRITTEN (nngp.py:49-62): a scikit-learn ``KDTree(s[0:i])`` rebuilt for
+    every i and queried for k = min(m, i) -- the same third-party calls, restated so that bench.py can
+    time the reference's own algorithm on the GPU box's host (where /root/reference does not exist).
+    tests/test_oracle.py checks it against the golden tables made by the unmodified reference."""
+    from sklearn.neighbors import KDTree
+
+    s = np.asarray(s)
+    Ns = []
+    for i, si in enumerate(s):
+        if i == 0:
+            Ns.append([])
+            continue
+        Ns.append(KDTree(s[0:i]).query(si.reshape(1, -1), k=min(m, i), return_distance=False)[0])
+    return Ns
+
+
 def ns_to_table(Ns, m):
     """list-of-arrays (reference layout) -> dense (n, m) int32 table padded with -1."""
     tab = np.full((len(Ns), m), -1, dtype=np.int32)

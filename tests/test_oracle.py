@@ -32,6 +32,18 @@ def test_knn_numpy_oracle_matches_reference_golden(golden_dir, name):
     assert np.array_equal(orc.ns_to_table(Ns, int(g["m"])), g["Ns"])
 
 
+@pytest.mark.parametrize("name", ["test_init_shape", "cfg1", "d1_m5", "lattice"])
+def test_sklearn_restatement_of_stage1_is_the_reference(golden_dir, name):
+    """oracle.sk_reference_stage1 makes the reference's own scikit-learn calls (nngp.py:55-61), so it must
+    reproduce the unmodified reference's tables exactly -- on the tied lattice too, where the KD-tree's
+    order among equal distances is whatever scikit-learn does.  bench.py times this function as the
+    reference's stage 1 on the GPU box's host."""
+    g = np.load(os.path.join(golden_dir, f"ns_{name}.npz"))
+    Ns = orc.sk_reference_stage1(g["coords"], int(g["m"]))
+    assert Ns[0] == []
+    assert np.array_equal(orc.ns_to_table(Ns, int(g["m"])), g["Ns"])
+
+
 def test_knn_lattice_ties_distance_multiset(golden_dir):
     """On tied inputs the reference's KD-tree order is unspecified: the oracle's
     (d2, j) rule must give the same multiset of neighbour distances per row."""
