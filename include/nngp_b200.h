@@ -85,7 +85,9 @@ int nngp_build_neighbors(nngp_handle *h, int m, int tile_offset, int tile_stride
  * histogram predicts more work than brute force; NNGP_KNN_GRID / NNGP_KNN_BRUTE force one. */
 enum { NNGP_KNN_AUTO = 0, NNGP_KNN_GRID = 1, NNGP_KNN_BRUTE = 2 };
 int nngp_build_neighbors_grid(nngp_handle *h, int m, int64_t row_lo, int64_t row_hi, int algo);
-/* Same search with the candidates of row i restricted to j < min(i, cand_cap).  With the n reference
+/* Same search with the candidates of row i restricted to j < min(i, cand_cap).  Replaces
+ * _make_t_neighbor_sets for S != T, nngp.py:68-71 (KDTree(s).query(t_i, m): the sites of t appended after
+ * the nRef rows of s, row_lo = cand_cap = nRef).  With the n reference
  * sites in rows [0, n) and q prediction sites appended as rows [n, n + q), row_lo = cand_cap = n gives
  * every new site its m nearest REFERENCE sites (the neighbour sets kriging conditions on; the step after
  * the path); nngp_factors over the same rows then returns the kriging weights and variances. */
