@@ -33,6 +33,23 @@ namespace nngp_fused {
 constexpr int kThreads = 128;
 constexpr int kWarps = kThreads / 32;
 
+#ifdef NNGP_TIMELINE
+static __device__ unsigned long long nngp_tl[64];
+static __device__ unsigned long long nngp_tl_blk[3][1024];  // per block: entry, loop done, smid
+__device__ __forceinline__ void tl_stamp(int slot, bool who)
+{
+    if (who) {
+        unsigned long long g;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g));
+        nngp_tl[slot] = g;
+        nngp_tl[32 + slot] = clock64();
+    }
+}
+#define TL(slot, who) tl_stamp(slot, who)
+#else
+#define TL(slot, who)
+#endif
+
 template <typename T, bool DIM3>
 struct StagePt;
 template <typename T>
@@ -373,6 +390,10 @@ __global__ void __launch_bounds__(kThreads, MINB) fused_loglik_kernel(const Eval
     using WS = WarpSmem<T, G, R, DIM3, BUILD>;
 
     extern __shared__ __align__(32) unsigned char smem_raw[];
+    TL(0, blockIdx.x == 0 && threadIdx.x == 0);
+#ifdef NNGP_TIMELINE
+    if (threadIdx.x == 0) { unsigned long long g_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g_)); nngp_tl_blk[0][blockIdx.x] = g_; unsigned int sm_; asm volatile("mov.u32 %0, %%smid;" : "=r"(sm_)); nngp_tl_blk[2][blockIdx.x] = sm_; }
+#endif
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const int q = lane % G;  // row residue owned by this lane
@@ -395,18 +416,39 @@ __global__ void __launch_bounds__(kThreads, MINB) fused_loglik_kernel(const Eval
 
     constexpr bool SWEEP = sweep_build<BUILD>();
     static_assert(!SWEEP || (sizeof(T) == 8 && !EMIT && ELIM == 1), "the sweep variant is fp64, reduction only");
+    // FACT: sigma2 is factored out of the matrix, C = sigma2 (R + delta I) with delta_i = (tau2 + eps2_i) / sigma2,
+    // and restored in the last block (sum log F = (n - n_bad) log sigma2 + sum log F', sum r^2/F = (sum r^2/F') /
+    // sigma2).  The exp table then carries no parameter: it is an asynchronous copy of the handle's 2^(j/2048)
+    // table that overlaps the first gather instead of a load-multiply-store pass every block waits for.  The
+    // emitting variant keeps sigma2 inside (its outputs are the covariances themselves), and so does fp32.
+    constexpr bool FACT = sizeof(T) == 8 && !EMIT;
     // sweep: blockIdx.y = chunk of parameter vectors [k0, k0 + kc); otherwise one vector per blockIdx.y
     const int k0 = SWEEP ? int(blockIdx.y) * kSweepChunk : int(blockIdx.y);
     const int kc = SWEEP ? (a.K - k0 < kSweepChunk ? a.K - k0 : kSweepChunk) : 1;
     const double *prm = a.params + size_t(k0) * NNGP_NPARAM;
-    const T sigma2 = SWEEP ? T(1) : T(prm[0]);
+    const T sigma2 = FACT ? T(1) : T(prm[0]);
     const double phi = SWEEP ? 1.0 : prm[1];  // sweep: coordinates stay unscaled, u = phi_k * distance per vector
-    const double diag0 = prm[0] + prm[2];
+    // {diagonal without eps2, scale of eps2}: read from shared memory where they are used -- the main loop is at
+    // its register limit and pays for every value kept live across it
+    __shared__ double s_diag[2];
+    if (threadIdx.x == 0) {
+        const double inv_s2 = FACT && !SWEEP ? 1.0 / prm[0] : 1.0;
+        s_diag[0] = FACT && !SWEEP ? fma(prm[2], inv_s2, 1.0) : prm[0] + prm[2];
+        s_diag[1] = inv_s2;
+    }
     const int m = a.m;
     constexpr int TB = exp_tab_bits<G, BUILD>();
-    if constexpr (sizeof(T) == 8)  // sigma2 * 2^(k / 2^TB) from the handle's table of 2^(j/2048): one L2 load and a multiply
-        for (int k = threadIdx.x; k < (1 << TB); k += kThreads)
-            exp_tab[k] = T(double(sigma2) * __ldg(a.exp2tab + (k << (11 - TB))));
+    if constexpr (sizeof(T) == 8) {
+        if constexpr (FACT && TB == 11) {
+            // 16 KB, 16 bytes per cp.async, L2-only (every block reads the same lines); completes under the
+            // prologue's first wait_group, published to the block by the __syncthreads below
+            for (int k = threadIdx.x; k < (1 << TB) / 2; k += kThreads)
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr(exp_tab + 2 * k)), "l"(a.exp2tab + 2 * k) : "memory");
+        } else {  // sigma2 * 2^(k / 2^TB) from the handle's table of 2^(j/2048): one L2 load and a multiply
+            for (int k = threadIdx.x; k < (1 << TB); k += kThreads)
+                exp_tab[k] = T(double(sigma2) * __ldg(a.exp2tab + (k << (11 - TB))));
+        }
+    }
     // sum log F is carried as log(prod of mantissas) + ln2 * (sum of exponents): one multiply and a few
     // integer operations per location instead of a log() the whole warp would issue for one lane in G
     int nbad = 0;
@@ -449,6 +491,7 @@ __global__ void __launch_bounds__(kThreads, MINB) fused_loglik_kernel(const Eval
         for (int k = lane; k < W * tile_stride<P>(); k += 32) tile_w[k] = T(0);
     }
     __syncthreads();
+    TL(1, blockIdx.x == 0 && threadIdx.x == 0);
 
     const int64_t nloc = a.hi - a.lo;
     const int64_t ngroups = (nloc + W - 1) / W;
@@ -499,6 +542,7 @@ __global__ void __launch_bounds__(kThreads, MINB) fused_loglik_kernel(const Eval
     issue_idx(grp0);
     asm volatile("cp.async.commit_group;" ::: "memory");
     asm volatile("cp.async.wait_group 0;" ::: "memory");
+    if constexpr (FACT && TB == 11) __syncthreads();  // every thread's slice of the exp table has landed
     issue_rec();
     issue_idx(grp0 + gstride);
     asm volatile("cp.async.commit_group;" ::: "memory");
@@ -513,6 +557,7 @@ __global__ void __launch_bounds__(kThreads, MINB) fused_loglik_kernel(const Eval
         // covariance build works directly on u^2 = (phi*d)^2.
         asm volatile("cp.async.wait_group 0;" ::: "memory");
         __syncwarp();
+        TL(2, blockIdx.x == 0 && threadIdx.x == 0 && grp == grp0);
         T rx[R], ry[R], rz[R], w[R], dg[R];
         T w0[R], e2r[R];  // sweep only: the untouched right-hand side and eps2 of the lane's rows
         bool valid[R];
@@ -521,6 +566,7 @@ __global__ void __launch_bounds__(kThreads, MINB) fused_loglik_kernel(const Eval
             const double2 self0 = recs[2 * (P - 1)];
             const double sx = self0.x, sy = self0.y;
             const double sz = DIM3 ? recs[2 * (P - 1) + 1].x : 0.0;
+            const double diag0 = s_diag[0], inv_s2 = s_diag[1];
 #pragma unroll
             for (int s = 0; s < R; ++s) {
                 const int r = s * G + q;
@@ -538,7 +584,7 @@ __global__ void __launch_bounds__(kThreads, MINB) fused_loglik_kernel(const Eval
                 ry[s] = valid[s] ? T((v0.y - sy) * phi) : T(0);
                 rz[s] = valid[s] ? T((v1.x - sz) * phi) : T(0);
                 w[s] = valid[s] ? T(v1.y) : T(0);
-                dg[s] = valid[s] ? T(diag0 + e2) : T(1);
+                dg[s] = valid[s] ? T(FACT && !SWEEP ? fma(e2, inv_s2, diag0) : diag0 + e2) : T(1);
                 w0[s] = w[s];
                 e2r[s] = T(e2);
                 Pt pt;
@@ -851,6 +897,11 @@ __global__ void __launch_bounds__(kThreads, MINB) fused_loglik_kernel(const Eval
         } while (SWEEP && ++kk < kc);  // parameter vectors (a single pass outside the sweep variant)
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");  // drain copies issued for groups past the end
+    TL(3, blockIdx.x == 0 && threadIdx.x == 0);
+#ifdef NNGP_TIMELINE
+    __syncthreads();
+    if (threadIdx.x == 0) { unsigned long long g_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g_)); nngp_tl_blk[1][blockIdx.x] = g_; }
+#endif
 
     // ---- reduction: warp shuffle tree -> block -> per-block partial -> last block sums ------
     // (one pass per parameter vector of the chunk; a single pass outside the sweep variant)
@@ -876,13 +927,16 @@ __global__ void __launch_bounds__(kThreads, MINB) fused_loglik_kernel(const Eval
             part[0] = s0; part[1] = s1; part[2] = s2;
         }
     }
+    TL(4, blockIdx.x == 0 && threadIdx.x == 0);
     if (threadIdx.x == 0) {
         __threadfence();
         const unsigned int ticket = atomicAdd(a.counters + blockIdx.y, 1u);
         is_last = (ticket == gridDim.x - 1);
     }
     __syncthreads();
+    TL(5, blockIdx.x == 0 && threadIdx.x == 0);
     if (is_last) {
+        TL(6, threadIdx.x == 0);
         __threadfence();
         double(*fin)[3] = reinterpret_cast<double(*)[3]>(smem_raw);  // main-loop buffers are dead here
         for (int kk = 0; kk < kc; ++kk) {
@@ -893,23 +947,25 @@ __global__ void __launch_bounds__(kThreads, MINB) fused_loglik_kernel(const Eval
                 t1 += __ldcg(part + size_t(b) * 3 + 1);
                 t2 += __ldcg(part + size_t(b) * 3 + 2);
             }
-            __syncthreads();
-            fin[threadIdx.x][0] = t0; fin[threadIdx.x][1] = t1; fin[threadIdx.x][2] = t2;
-            __syncthreads();
-            for (int stride = kThreads / 2; stride > 0; stride >>= 1) {
-                if (threadIdx.x < stride) {
-                    fin[threadIdx.x][0] += fin[threadIdx.x + stride][0];
-                    fin[threadIdx.x][1] += fin[threadIdx.x + stride][1];
-                    fin[threadIdx.x][2] += fin[threadIdx.x + stride][2];
-                }
-                __syncthreads();
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {  // fixed tree: deterministic for a given grid
+                t0 += __shfl_xor_sync(0xffffffffu, t0, off);
+                t1 += __shfl_xor_sync(0xffffffffu, t1, off);
+                t2 += __shfl_xor_sync(0xffffffffu, t2, off);
             }
-            double tot[3] = {fin[0][0], fin[0][1], fin[0][2]};
-            if constexpr (SWEEP) {
+            __syncthreads();  // fin[] of the previous pass (and the main loop's buffers) are no longer read
+            if (lane == 0) { fin[warp][0] = t0; fin[warp][1] = t1; fin[warp][2] = t2; }
+            __syncthreads();
+            double tot[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+            for (int wv = 0; wv < kWarps; ++wv) { tot[0] += fin[wv][0]; tot[1] += fin[wv][1]; tot[2] += fin[wv][2]; }
+            if constexpr (FACT) {
                 // restore sigma2: F = sigma2 F' on the (n - n_bad) locations that entered the sums
                 const double good = double(a.hi - a.lo) - tot[2];
-                tot[0] = fma(good, sw_prm[kk][3], tot[0]);
-                tot[1] *= sw_prm[kk][2];
+                const double ls2 = SWEEP ? sw_prm[kk][3] : log(prm[0]);
+                const double is2 = SWEEP ? sw_prm[kk][2] : 1.0 / prm[0];
+                tot[0] = fma(good, ls2, tot[0]);
+                tot[1] *= is2;
             }
             if (a.px.world > 1) {  // sum over the ranks through NVLink peer memory (block-uniform branch)
                 __syncthreads();
@@ -922,6 +978,7 @@ __global__ void __launch_bounds__(kThreads, MINB) fused_loglik_kernel(const Eval
             }
         }
         if (threadIdx.x == 0) a.counters[blockIdx.y] = 0u;  // ready for the next launch
+        TL(7, threadIdx.x == 0);
     }
 }
 
