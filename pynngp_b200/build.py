@@ -58,8 +58,8 @@ def _compile(src, verbose):
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"nvcc failed on {src}:\n{r.stdout}\n{r.stderr}")
-    with open(obj.replace(".o", ".ptxas.log"), "w") as f:
-        f.write(r.stderr)
+    with open(obj.replace(".o", ".ptxas.log"), "w") as f:  # registers / spills per kernel; timings dropped (they churn)
+        f.write("".join(l for l in r.stderr.splitlines(True) if "Compile time" not in l))
     return obj, r.stderr if verbose else ""
 
 
