@@ -438,8 +438,11 @@ __global__ void __launch_bounds__(kThreads, MINB) fused_loglik_kernel(const Eval
     }
     const int m = a.m;
     constexpr int TB = exp_tab_bits<G, BUILD>();
+    // (the sweep variant keeps the synchronous fill: its launches are long, and its register allocation is too
+    // finely balanced to touch -- the asynchronous form cost it 10 % in spills)
+    constexpr bool ASYNC_TAB = FACT && TB == 11 && !SWEEP;
     if constexpr (sizeof(T) == 8) {
-        if constexpr (FACT && TB == 11) {
+        if constexpr (ASYNC_TAB) {
             // 16 KB, 16 bytes per cp.async, L2-only (every block reads the same lines); completes under the
             // prologue's first wait_group, published to the block by the __syncthreads below
             for (int k = threadIdx.x; k < (1 << TB) / 2; k += kThreads)
@@ -542,7 +545,7 @@ __global__ void __launch_bounds__(kThreads, MINB) fused_loglik_kernel(const Eval
     issue_idx(grp0);
     asm volatile("cp.async.commit_group;" ::: "memory");
     asm volatile("cp.async.wait_group 0;" ::: "memory");
-    if constexpr (FACT && TB == 11) __syncthreads();  // every thread's slice of the exp table has landed
+    if constexpr (ASYNC_TAB) __syncthreads();  // every thread's slice of the exp table has landed
     issue_rec();
     issue_idx(grp0 + gstride);
     asm volatile("cp.async.commit_group;" ::: "memory");
@@ -566,7 +569,7 @@ __global__ void __launch_bounds__(kThreads, MINB) fused_loglik_kernel(const Eval
             const double2 self0 = recs[2 * (P - 1)];
             const double sx = self0.x, sy = self0.y;
             const double sz = DIM3 ? recs[2 * (P - 1) + 1].x : 0.0;
-            const double diag0 = s_diag[0], inv_s2 = s_diag[1];
+            const double diag0 = SWEEP ? 1.0 : s_diag[0], inv_s2 = SWEEP ? 1.0 : s_diag[1];  // sweep: set per vector below
 #pragma unroll
             for (int s = 0; s < R; ++s) {
                 const int r = s * G + q;
@@ -947,25 +950,58 @@ __global__ void __launch_bounds__(kThreads, MINB) fused_loglik_kernel(const Eval
                 t1 += __ldcg(part + size_t(b) * 3 + 1);
                 t2 += __ldcg(part + size_t(b) * 3 + 2);
             }
+            double tot[3];
+            // Both trees are fixed: deterministic for a given grid.  (Two forms on purpose: ptxas allocates the
+            // whole kernel at once, and giving the sweep variant the shuffle tree below costs its main loop
+            // 40 bytes of spill traffic per iteration -- 10 % of its run time.)
+            if constexpr (SWEEP) {
+                __syncthreads();
+                fin[threadIdx.x][0] = t0; fin[threadIdx.x][1] = t1; fin[threadIdx.x][2] = t2;
+                __syncthreads();
+                for (int stride = kThreads / 2; stride > 0; stride >>= 1) {
+                    if (threadIdx.x < stride) {
+                        fin[threadIdx.x][0] += fin[threadIdx.x + stride][0];
+                        fin[threadIdx.x][1] += fin[threadIdx.x + stride][1];
+                        fin[threadIdx.x][2] += fin[threadIdx.x + stride][2];
+                    }
+                    __syncthreads();
+                }
+                tot[0] = fin[0][0]; tot[1] = fin[0][1]; tot[2] = fin[0][2];
+            } else {  // one launch = one evaluation: the tail is part of the fixed cost, so it is kept short
 #pragma unroll
-            for (int off = 16; off > 0; off >>= 1) {  // fixed tree: deterministic for a given grid
-                t0 += __shfl_xor_sync(0xffffffffu, t0, off);
-                t1 += __shfl_xor_sync(0xffffffffu, t1, off);
-                t2 += __shfl_xor_sync(0xffffffffu, t2, off);
+                for (int off = 16; off > 0; off >>= 1) {
+                    t0 += __shfl_xor_sync(0xffffffffu, t0, off);
+                    t1 += __shfl_xor_sync(0xffffffffu, t1, off);
+                    t2 += __shfl_xor_sync(0xffffffffu, t2, off);
+                }
+                __syncthreads();  // the main loop's buffers are no longer read
+                if ((threadIdx.x & 31) == 0) { fin[threadIdx.x >> 5][0] = t0; fin[threadIdx.x >> 5][1] = t1; fin[threadIdx.x >> 5][2] = t2; }
+                __syncthreads();
+                tot[0] = 0.0; tot[1] = 0.0; tot[2] = 0.0;
+#pragma unroll
+                for (int wv = 0; wv < kWarps; ++wv) { tot[0] += fin[wv][0]; tot[1] += fin[wv][1]; tot[2] += fin[wv][2]; }
             }
-            __syncthreads();  // fin[] of the previous pass (and the main loop's buffers) are no longer read
-            if (lane == 0) { fin[warp][0] = t0; fin[warp][1] = t1; fin[warp][2] = t2; }
-            __syncthreads();
-            double tot[3] = {0.0, 0.0, 0.0};
-#pragma unroll
-            for (int wv = 0; wv < kWarps; ++wv) { tot[0] += fin[wv][0]; tot[1] += fin[wv][1]; tot[2] += fin[wv][2]; }
             if constexpr (FACT) {
                 // restore sigma2: F = sigma2 F' on the (n - n_bad) locations that entered the sums
                 const double good = double(a.hi - a.lo) - tot[2];
-                const double ls2 = SWEEP ? sw_prm[kk][3] : log(prm[0]);
-                const double is2 = SWEEP ? sw_prm[kk][2] : 1.0 / prm[0];
+                double ls2, is2;
+                if constexpr (SWEEP) {
+                    ls2 = sw_prm[kk][3];
+                    is2 = sw_prm[kk][2];
+                } else {
+                    // the parameter pointer is rebuilt from %ctaid here on purpose: carried from the top of the
+                    // kernel it stays live across the main loop, which is at its register limit and spills for it
+                    unsigned int by_;
+                    asm volatile("mov.u32 %0, %%ctaid.y;" : "=r"(by_));
+                    const double s2 = a.params[size_t(by_) * NNGP_NPARAM];
+                    ls2 = log(s2);
+                    is2 = 1.0 / s2;
+                }
                 tot[0] = fma(good, ls2, tot[0]);
                 tot[1] *= is2;
+                // sigma2 must be positive and finite to be factored out: otherwise every location counts as
+                // bad (the contract is a count, never a NaN)
+                if (!(is2 > 0.0 && is2 < INFINITY)) { tot[0] = 0.0; tot[1] = 0.0; tot[2] = double(a.hi - a.lo); }
             }
             if (a.px.world > 1) {  // sum over the ranks through NVLink peer memory (block-uniform branch)
                 __syncthreads();

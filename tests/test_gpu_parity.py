@@ -351,6 +351,24 @@ def test_non_spd_counted_not_nan():
     assert st[2] == st0[2]
 
 
+def test_nonpositive_sigma2_counted_not_nan():
+    """sigma2 is factored out of the matrix in the fp64 reduction kernels: a non-positive or non-finite
+    sigma2 must come back as 'every location bad', not as NaN -- one vector, a sweep, and the rolled shape."""
+    for n, D, m in ((3000, 2, 15), (1200, 3, 30), (500, 2, 5)):
+        s, y = synthetic(n, D, 3)
+        e = engine(s, y)
+        e.build_neighbors(m)
+        good = np.array([1.0, 6.0, 0.1, 0.0])
+        want = e.loglik(1, good)[0]
+        for bad_s2 in (0.0, -1.0, np.inf, np.nan):
+            st = e.loglik(1, np.array([bad_s2, 6.0, 0.1, 0.0]))[0]
+            assert np.array_equal(st, [0.0, 0.0, float(n)]), (m, bad_s2, st)
+            both = e.loglik(1, np.array([good, [bad_s2, 6.0, 0.1, 0.0], good]))
+            assert np.array_equal(both[1], [0.0, 0.0, float(n)])
+            np.testing.assert_allclose(both[0], want, rtol=1e-12)
+            np.testing.assert_allclose(both[2], want, rtol=1e-12)
+
+
 def test_set_y_replaces_response():
     s, y = synthetic(3000, 2, 3)
     nbr = orc.c_knn_ordered(s, 8)
