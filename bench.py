@@ -193,6 +193,9 @@ def run_ours(args, cfg):
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run")
     torch.cuda.set_device(local)
     if world > 1:
+        # NCCL's own messages (its version banner under NCCL_DEBUG=VERSION/INFO) go to stderr: stdout carries
+        # the one JSON line and nothing else
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     s, y = synthetic(cfg["n"], cfg["D"], cfg["seed"])
