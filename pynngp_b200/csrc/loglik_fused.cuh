@@ -160,12 +160,16 @@ __device__ __forceinline__ double scaled_exp_neg(double u, const double *tab, do
 template <int TB>
 __device__ __forceinline__ float scaled_exp_neg(float u, const float *, float sigma2)
 {
-    const float kf = rintf(u * -1.4426950408889634f);
+    // k = round(-u / ln2) by the magic-number add (1.5 * 2^23): the sum's low mantissa bits are k itself, so
+    // neither the rounding nor the float -> int conversion goes to the XU pipe, which the two MUFUs of a
+    // pair (rsqrt, ex2) already load (ncu: XU 58 % active with FRND + F2I here, the busiest pipe of the kernel)
+    const float t = fmaf(u, -1.4426950408889634f, 12582912.0f);
+    const float kf = t - 12582912.0f;
     float r = fmaf(kf, -0.693145751953125f, -u);
     r = fmaf(kf, -1.428606765330187e-06f, r);
     float e;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(r * 1.4426950408889634f));
-    const float v = sigma2 * e * __int_as_float((int(kf) + 127) << 23);
+    const float v = sigma2 * e * __int_as_float((__float_as_int(t) << 23) + 0x3f800000);  // * 2^k, |k| <= 126 below
     return u >= 87.0f ? 0.0f : v;
 }
 
