@@ -122,13 +122,15 @@ def oracle_sample_rate(s, y, m, kid, threads, sample, min_seconds):
     return per_loc * n, f"{hi - lo} contiguous rows [{lo},{hi}) x {reps} reps, scaled to n={n}"
 
 
-def reference_stage1_timing(cfg, sizes=(1000, 2000, 4000)):
+def reference_stage1_timing(cfg, sizes=None):
     """The reference's stage 1 as written (nngp.py:49-62: a scikit-learn KD-tree rebuilt for every i) timed
     on this host at small n -- the only part of the path the reference implements, single-threaded by
     construction -- with the quadratic extrapolation to the workload's n (x3.4-4.0 per
     doubling).  A few seconds of CPU work."""
     from oracle import nngp_oracle as orc  # the checker's restatement of the reference's own calls
 
+    if sizes is None:  # NNGP_BENCH_STAGE1_SIZES=200,400 shortens it (the CPU test of this arm's JSON contract)
+        sizes = tuple(int(k) for k in os.environ.get("NNGP_BENCH_STAGE1_SIZES", "1000,2000,4000").split(","))
     s, _ = synthetic(max(sizes), cfg["D"], cfg["seed"])
     orc.sk_reference_stage1(s[:200], cfg["m"])  # untimed: imports scikit-learn and warms its first call
     secs = []
@@ -150,6 +152,8 @@ def run_reference(args, cfg):
     threads = os.cpu_count() or 1
     kid = KIDS[cfg["kernel"]]
     per_step_budget = max(1.0, min(20.0, 120.0 / max(1, args.steps + args.warmup)))
+    if args.cpu_seconds is not None:
+        per_step_budget = args.cpu_seconds
     for _ in range(args.warmup):
         oracle_sample_rate(s[:200000], y[:200000], cfg["m"], kid, threads, 2048, 0.2)
     times, sample = [], ""
@@ -424,6 +428,7 @@ def main():
     ap.add_argument("--config", default="cfg3", choices=sorted(CONFIGS))
     ap.add_argument("--dtype", default="float64", choices=["float64", "float32"])
     ap.add_argument("--cpu-sample", type=int, default=16384)
+    ap.add_argument("--cpu-seconds", type=float, default=None, help="--impl reference: seconds of CPU work per step (default: 120 s over all steps, at most 20 s each)")
     ap.add_argument("--nccl-allreduce", action="store_true", help="multi-GPU: sum the statistics with NCCL instead of the fused peer-memory exchange")
     args = ap.parse_args()
     cfg = CONFIGS[args.config]

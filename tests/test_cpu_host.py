@@ -136,3 +136,39 @@ def test_two_rank_gloo_combination(tmp_path):
         env=env, capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
     assert r.stdout.count("ok") == 2
+
+
+def test_bench_work_model_matches_the_survey():
+    """bench.py's algorithmic figures are SURVEY 8(d4)'s: FP64-pipe instructions and compulsory HBM bytes per
+    location at the four configurations."""
+    import bench
+
+    assert bench.fp64_instr_per_location(10, 2, "exponential") == 2301
+    assert bench.fp64_instr_per_location(15, 2, "exponential") == 5056
+    assert bench.fp64_instr_per_location(15, 2, "matern32") == 5176
+    assert bench.fp64_instr_per_location(30, 3, "matern32") == 22716
+    assert [bench.hbm_bytes_per_location(m, D) for m, D in ((10, 2), (15, 2), (30, 3))] == [64, 84, 152]
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside the GPU arm): one JSON line on stdout
+    with the contract's keys; shortened here through --cpu-seconds / NNGP_BENCH_STAGE1_SIZES."""
+    import json
+
+    env = dict(os.environ, NNGP_BENCH_STAGE1_SIZES="150,300")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--config", "cfg2", "--steps", "1",
+                        "--warmup", "0", "--cpu-sample", "1024", "--cpu-seconds", "0.3"],
+                       env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "nngp_loglik_evals_per_sec" and d["unit"] == "evals/s"
+    assert d["higher_is_better"] is True and d["value"] > 0 and d["n_gpus"] == 1
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["cpu_baseline"]["stage1_reference"]["n"] == [150, 300]
+    # ranks other than 0 print nothing and exit 0
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2"],
+                       env=dict(env, RANK="1", WORLD_SIZE="2"), capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and r.stdout.strip() == ""
