@@ -186,7 +186,7 @@ void nngp_destroy(nngp_handle *h)
     if (!h) return;
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
-    free_dev(h->pts); free_dev(h->eps2); free_dev(h->nbr);
+    free_dev(h->pts); free_dev(h->eps2); free_dev(h->nbr); free_dev(h->d_ystage);
     free_dev(h->d_params); free_dev(h->d_out); free_dev(h->d_partials);
     free_dev(h->d_counters); free_dev(h->d_tile_counter); free_dev(h->d_exp2tab);
     for (int r = 0; r < NNGP_MAX_PEERS; ++r)
@@ -204,7 +204,7 @@ int nngp_set_data(nngp_handle *h, const double *coords, int64_t n, int D, const 
     if (n < 1 || n > 2147483647LL) return fail(h, NNGP_EINVAL, "n must be in [1, 2^31)");
     if (D < 1 || D > NNGP_MAX_D) return fail(h, NNGP_EINVAL, "D must be 1, 2 or 3");
     CUDA_TRY(h, cudaSetDevice(h->device));
-    free_dev(h->pts); free_dev(h->eps2); free_dev(h->nbr);
+    free_dev(h->pts); free_dev(h->eps2); free_dev(h->nbr); free_dev(h->d_ystage);  // the landing buffer is sized by n
     h->has_nbr = false; h->m = 0;
     h->n = n; h->D = D; h->lo = 0; h->hi = n;
     // raw arrays up, packed into {x, y, z, yval} records on the device (pack.cu), which also reduces the
@@ -238,9 +238,10 @@ int nngp_set_y(nngp_handle *h, const double *y)
     if (!h->pts) return fail(h, NNGP_ESTATE, "nngp_set_data has not been called");
     if (!y) return fail(h, NNGP_EINVAL, "y must not be NULL");
     CUDA_TRY(h, cudaSetDevice(h->device));
-    // strided copy into the .w lane of the records
-    CUDA_TRY(h, cudaMemcpy2DAsync(reinterpret_cast<double *>(h->pts) + 3, sizeof(double4), y, sizeof(double),
-                                  sizeof(double), (size_t)h->n, cudaMemcpyHostToDevice, h->stream));
+    // one contiguous copy, then a kernel writes the yval lane of the records (pack.cu)
+    if (!h->d_ystage) CUDA_TRY(h, cudaMalloc(&h->d_ystage, sizeof(double) * (size_t)h->n));
+    CUDA_TRY(h, cudaMemcpyAsync(h->d_ystage, y, sizeof(double) * (size_t)h->n, cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(h, launch_scatter_y(h, h->d_ystage, h->stream));
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     return NNGP_OK;
 }

@@ -47,6 +47,7 @@ struct nngp_handle {
     int64_t knn_brute_rows = 4096;                       // grid k-NN: rows below this use brute force
 
     double4 *pts = nullptr;
+    double *d_ystage = nullptr;  // n doubles: landing buffer of nngp_set_y (allocated on first use)
     double *eps2 = nullptr;
     int32_t *nbr = nullptr;
     bool has_nbr = false;
@@ -95,6 +96,8 @@ struct EvalArgs {
 // launchers implemented in the .cu files; each returns the cudaError of the launch.
 cudaError_t launch_fused_loglik(nngp_handle *h, int kernel_id, const EvalArgs &a, int K,
                                 cudaStream_t stream);
+// y (n doubles, device) -> the yval lane of the records
+cudaError_t launch_scatter_y(nngp_handle *h, const double *d_y, cudaStream_t stream);
 cudaError_t launch_knn_ordered(nngp_handle *h, int m, int tile_offset, int tile_stride,
                                cudaStream_t stream);
 cudaError_t launch_knn_plain(nngp_handle *h, int k, int32_t *d_table, cudaStream_t stream);
