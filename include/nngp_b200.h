@@ -63,6 +63,10 @@ int nngp_set_data(nngp_handle *h, const double *coords, int64_t n, int D, const 
                   const double *eps2);
 /* Replaces y only (n fp64), keeping coordinates and neighbours. */
 int nngp_set_y(nngp_handle *h, const double *y);
+/* Replaces the per-observation variances only (n fp64, the square of nngp.py:9's `eps`), keeping coordinates,
+ * y and neighbours.  A latent-field density (reference sites carry no nugget, observations do) changes these
+ * with tau2 while everything else stays resident. */
+int nngp_set_eps2(nngp_handle *h, const double *eps2);
 
 /* Rows [lo, hi) of the ordering are this handle's shard: stages 2-3 and the returned partial
  * statistics cover exactly these rows.  Coordinates / y stay replicated in full. */

@@ -32,6 +32,7 @@ SIGNATURES = {
     "nngp_destroy": (None, [_handle_p]),
     "nngp_set_data": (ctypes.c_int, [_handle_p, _c_double_p, ctypes.c_int64, ctypes.c_int, _c_double_p, _c_double_p]),
     "nngp_set_y": (ctypes.c_int, [_handle_p, _c_double_p]),
+    "nngp_set_eps2": (ctypes.c_int, [_handle_p, _c_double_p]),
     "nngp_set_shard": (ctypes.c_int, [_handle_p, ctypes.c_int64, ctypes.c_int64]),
     "nngp_build_neighbors": (ctypes.c_int, [_handle_p, ctypes.c_int, ctypes.c_int, ctypes.c_int]),
     "nngp_build_neighbors_grid": (ctypes.c_int, [_handle_p, ctypes.c_int, ctypes.c_int64, ctypes.c_int64, ctypes.c_int]),
@@ -136,6 +137,10 @@ class Engine:
     def set_y(self, y):
         y = _f64(y, (self.n,))
         self._check(self._lib.nngp_set_y(self._h, _dp(y)), "nngp_set_y")
+
+    def set_eps2(self, eps2):
+        eps2 = _f64(eps2, (self.n,))
+        self._check(self._lib.nngp_set_eps2(self._h, _dp(eps2)), "nngp_set_eps2")
 
     def set_shard(self, lo, hi):
         self._check(self._lib.nngp_set_shard(self._h, int(lo), int(hi)), "nngp_set_shard")

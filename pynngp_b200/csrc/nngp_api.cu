@@ -241,7 +241,25 @@ int nngp_set_y(nngp_handle *h, const double *y)
     // one contiguous copy, then a kernel writes the yval lane of the records (pack.cu)
     if (!h->d_ystage) CUDA_TRY(h, cudaMalloc(&h->d_ystage, sizeof(double) * (size_t)h->n));
     CUDA_TRY(h, cudaMemcpyAsync(h->d_ystage, y, sizeof(double) * (size_t)h->n, cudaMemcpyHostToDevice, h->stream));
-    CUDA_TRY(h, launch_scatter_y(h, h->d_ystage, h->stream));
+    CUDA_TRY(h, launch_scatter_lane(h, h->d_ystage, 3, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return NNGP_OK;
+}
+
+int nngp_set_eps2(nngp_handle *h, const double *eps2)
+{
+    if (!h) return fail(nullptr, NNGP_EINVAL, "null handle");
+    if (!h->pts) return fail(h, NNGP_ESTATE, "nngp_set_data has not been called");
+    if (!eps2) return fail(h, NNGP_EINVAL, "eps2 must not be NULL");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    if (h->D > 2) {  // D = 3: its own array (the records' z slot holds a coordinate)
+        if (!h->eps2) CUDA_TRY(h, cudaMalloc(&h->eps2, sizeof(double) * (size_t)h->n));
+        CUDA_TRY(h, cudaMemcpyAsync(h->eps2, eps2, sizeof(double) * (size_t)h->n, cudaMemcpyHostToDevice, h->stream));
+    } else {         // D < 3: the records' z slot
+        if (!h->d_ystage) CUDA_TRY(h, cudaMalloc(&h->d_ystage, sizeof(double) * (size_t)h->n));
+        CUDA_TRY(h, cudaMemcpyAsync(h->d_ystage, eps2, sizeof(double) * (size_t)h->n, cudaMemcpyHostToDevice, h->stream));
+        CUDA_TRY(h, launch_scatter_lane(h, h->d_ystage, 2, h->stream));
+    }
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     return NNGP_OK;
 }

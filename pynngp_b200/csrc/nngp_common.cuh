@@ -96,8 +96,8 @@ struct EvalArgs {
 // launchers implemented in the .cu files; each returns the cudaError of the launch.
 cudaError_t launch_fused_loglik(nngp_handle *h, int kernel_id, const EvalArgs &a, int K,
                                 cudaStream_t stream);
-// y (n doubles, device) -> the yval lane of the records
-cudaError_t launch_scatter_y(nngp_handle *h, const double *d_y, cudaStream_t stream);
+// v (n doubles, device) -> lane `lane` of the records (3 = yval; 2 = eps2 when D < 3)
+cudaError_t launch_scatter_lane(nngp_handle *h, const double *d_v, int lane, cudaStream_t stream);
 cudaError_t launch_knn_ordered(nngp_handle *h, int m, int tile_offset, int tile_stride,
                                cudaStream_t stream);
 cudaError_t launch_knn_plain(nngp_handle *h, int k, int32_t *d_table, cudaStream_t stream);

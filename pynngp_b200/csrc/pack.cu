@@ -57,20 +57,21 @@ __global__ void __launch_bounds__(kBlock) pack_records_kernel(const double *__re
 
 // nngp_set_y: the new response arrives as one contiguous copy and is written into the records' yval lane here
 // (a strided 8-byte-per-row cudaMemcpy2D of the same data is n separate DMA rows: milliseconds at n = 1e6)
-__global__ void __launch_bounds__(kBlock) scatter_y_kernel(const double *__restrict__ y, int64_t n, double4 *__restrict__ pts)
+__global__ void __launch_bounds__(kBlock) scatter_lane_kernel(const double *__restrict__ v, int64_t n, int lane,
+                                                               double4 *__restrict__ pts)
 {
     for (int64_t i = blockIdx.x * int64_t(kBlock) + threadIdx.x; i < n; i += int64_t(gridDim.x) * kBlock)
-        reinterpret_cast<double *>(pts + i)[3] = y[i];
+        reinterpret_cast<double *>(pts + i)[lane] = v[i];
 }
 
 }  // namespace nngp_pack
 
-cudaError_t launch_scatter_y(nngp_handle *h, const double *d_y, cudaStream_t stream)
+cudaError_t launch_scatter_lane(nngp_handle *h, const double *d_v, int lane, cudaStream_t stream)
 {
     using namespace nngp_pack;
     int grid = int(std::min<int64_t>((h->n + kBlock - 1) / kBlock, int64_t(h->num_sms) * 8));
     if (grid < 1) grid = 1;
-    scatter_y_kernel<<<grid, kBlock, 0, stream>>>(d_y, h->n, h->pts);
+    scatter_lane_kernel<<<grid, kBlock, 0, stream>>>(d_v, h->n, lane, h->pts);
     ++h->launches;
     return cudaGetLastError();
 }

@@ -216,6 +216,7 @@ class NNGP(object):
                               y2d.shape)
         eps2 = None if not np.any(eps) else np.ascontiguousarray(eps * eps)
         self._yt2d = y2d  # the response in the order of t (what `ws` averages)
+        self._eps2_t = eps2  # eps^2 in the order of t, or None
         self._rows = None  # engine row -> row of t
         if self._ref_kind == "subset":
             t = as2d(self.t)
@@ -488,6 +489,46 @@ class NNGP(object):
         slog, squad = self.loglik_terms(sigma2, phi, tau2)
         ncol = self._y2d.shape[1]
         return -0.5 * (slog + squad) - 0.5 * len(self._coords) * ncol * LOG_2PI
+
+    def loglik_latent(self, w_s, sigma2=None, phi=None, tau2=None):
+        """Joint log density of the latent NNGP model the reference's sampler is meant to explore (its
+        ``oneSample`` would update ``wt`` / ``ws``, nngp.py:98-101): log p(w_S) + log p(y | w_S) with
+
+            p(w_S)     = prod_i N(w_i | b_i^T w_N(s_i), F_i),   C = sigma2 rho, no nugget on the latent field,
+            p(y | w_S) = prod_t N(y_t | b_t^T w_N(t), sigma2 + tau2 + eps_t^2 - c_t^T C_N(t)^-1 c_t),
+
+        N(s_i) from ``Ns`` and N(t) from ``Nt``.  Works for every refType ('random' included: this is the
+        density that needs no response at the reference sites).  One launch of the fused kernel per response
+        column over the rows [s ; t] of a second engine (built on first use): the latent values ride in the
+        response lane of the reference rows, and the nugget tau2 + eps_t^2 is the per-observation variance of
+        the observation rows only (``nngp_set_eps2``), so the kernel's own tau2 stays 0.  Every rank evaluates
+        the whole density (no sharding)."""
+        prm = self._params(sigma2, phi, tau2)
+        n_ref, nt, ncol = self._n_ref, self._yt2d.shape[0], self._yt2d.shape[1]
+        w = np.asarray(w_s, dtype=np.float64).reshape(n_ref, -1)
+        if w.shape[1] != ncol:
+            raise ValueError("w_s must hold one latent value per reference site and response column")
+        eng = getattr(self, "_latent_eng", None)
+        if eng is None:
+            t = np.ascontiguousarray(self.t, dtype=np.float64)
+            t = t[:, None] if t.ndim == 1 else t
+            eng = _lib.Engine(device=self._engine.device, dtype=self._engine.dtype)
+            eng.set_data(np.concatenate([self._coords_s(), t]), np.zeros(n_ref + nt), None)
+            eng.set_neighbors(np.concatenate([self._table[:n_ref], self._nt_table]))
+            self._latent_eng, self._latent_nugget = eng, None
+        total = 0.0
+        for c in range(ncol):
+            nugget = (float(prm[2]), c if self._eps2_t is not None else 0)
+            if self._latent_nugget != nugget:  # the observation rows' variances change with tau2 (and the column's eps)
+                e2 = np.full(nt, prm[2]) if self._eps2_t is None else prm[2] + self._eps2_t[:, c]
+                eng.set_eps2(np.concatenate([np.zeros(n_ref), e2]))
+                self._latent_nugget = nugget
+            eng.set_y(np.concatenate([w[:, c], self._yt2d[:, c]]))
+            st = eng.loglik(self._kernel.kernel_id, np.array([prm[0], prm[1], 0.0, 0.0]))[0]
+            if st[2] > 0:
+                raise FloatingPointError(f"{int(st[2])} location(s) had a non-positive-definite neighbour covariance")
+            total += st[0] + st[1]
+        return -0.5 * total - 0.5 * (n_ref + nt) * ncol * LOG_2PI
 
     # ---- either side of the path: table I/O, kriging at new sites, a sweep driver ---------------------
     def save_neighbors(self, path):

@@ -59,6 +59,11 @@ class FakeEngine:
         assert y.shape == (self.n,)
         self._y = y
 
+    def set_eps2(self, eps2):
+        eps2 = np.ascontiguousarray(eps2, dtype=np.float64)
+        assert eps2.shape == (self.n,)
+        self._eps2 = eps2
+
     def set_shard(self, lo, hi):
         assert 0 <= lo <= hi <= self.n
         self._shard = (int(lo), int(hi))

@@ -140,3 +140,54 @@ def check_ref_type_errors(make, t, y):
         make(t, y, 0.0, ("subset", len(t) + 1), 3, seed=0)
     with pytest.raises(ValueError):
         make(t, y, 0.0, ("random", 10, ((0, 1),) * (t.shape[1] + 1)), 3, seed=0)
+
+
+def _latent_expected(s, w, t, y, m, kernel_id, prm, eps2_t=None):
+    """log p(w_S) + log p(y | w_S) computed without the engine's row layout: the oracle's NNGP density of w on s
+    (no nugget) plus, per observation, the kriging density from its m nearest reference sites (oracle.np_krige)."""
+    s_tab = orc.c_knn_ordered(s, m)
+    slog, squad, bad = orc.c_loglik(s, w, s_tab, kernel_id, prm[0], prm[1], 0.0)
+    assert bad == 0
+    ll = -0.5 * (slog + squad) - 0.5 * len(s) * np.log(2 * np.pi)
+    mean, var, _ = orc.np_krige(s, w, t, m, kernel_id, prm[0], prm[1], 0.0)  # var = sigma2 - c^T C_N^-1 c
+    F = var + prm[2] + (0.0 if eps2_t is None else eps2_t)
+    return ll + float(np.sum(-0.5 * np.log(2 * np.pi * F) - 0.5 * (y - mean) ** 2 / F))
+
+
+LATENT_RTOL = 1e-8  # no nugget on the latent field: F_i of close reference sites cancels down to ~1e-6 sigma2
+
+
+def check_latent_density(make, t, y, m, kernel_id, prm, seed=5):
+    """loglik_latent for the three reference-set types, against the layout-free restatement above."""
+    n, D = t.shape
+    rng = np.random.default_rng(seed)
+    kw = dict(sigma2=prm[0], phi=prm[1], tau2=prm[2])
+    # S = T
+    obj = make(t, y, 0.0, "S=T", m)
+    w = y + 0.1 * rng.standard_normal(n)
+    np.testing.assert_allclose(obj.loglik_latent(w, **kw), _latent_expected(t, w, t, y, m, kernel_id, prm), rtol=LATENT_RTOL)
+    # subset, with per-observation eps, evaluated at two nuggets (the second call reuses the resident rows)
+    eps = np.linspace(0.05, 0.3, n)
+    sub = make(t, y, eps, ("subset", max(m + 2, n // 3)), m, seed=seed)
+    ws = np.asarray(sub.ws, dtype=np.float64)
+    for tau2 in (prm[2], 2.5 * prm[2]):
+        want = _latent_expected(sub.s, ws, t, y, m, kernel_id, (prm[0], prm[1], tau2), eps2_t=eps ** 2)
+        np.testing.assert_allclose(sub.loglik_latent(ws, prm[0], prm[1], tau2), want, rtol=LATENT_RTOL)
+    # random: no response at the reference sites, the latent density is the one that exists
+    bounds = tuple((0.0, 1.0) for _ in range(D))
+    rnd = make(t, y, 0.0, ("random", max(m + 2, n // 4), bounds), m, seed=seed)
+    wr = np.asarray(rnd.ws, dtype=np.float64)
+    np.testing.assert_allclose(rnd.loglik_latent(wr, **kw), _latent_expected(rnd.s, wr, t, y, m, kernel_id, prm), rtol=LATENT_RTOL)
+    with pytest.raises(ValueError):
+        rnd.loglik_latent(wr[:-1], **kw)
+
+
+def check_latent_dense_identity(make, t, y, kernel_id, prm):
+    """Closed form for S = T with m = n - 1: the dense GP density of w (no nugget) plus independent
+    N(y_i | w_i, tau2) terms -- every observation's nearest reference site is itself."""
+    n = len(t)
+    obj = make(t, y, 0.0, "S=T", n - 1)
+    w = 0.7 * y + 0.05
+    want = orc.dense_gp_loglik(t, w, kernel_id, prm[0], prm[1], 0.0) + float(
+        np.sum(-0.5 * np.log(2 * np.pi * prm[2]) - 0.5 * (y - w) ** 2 / prm[2]))
+    np.testing.assert_allclose(obj.loglik_latent(w, *prm), want, rtol=1e-8)

@@ -68,3 +68,17 @@ def test_ref_type_errors_and_injected_table():
     assert a.loglik() == b.loglik()
     slog, squad, _ = orc.c_loglik(t[a._rows], y[a._rows], a._table, 1, *PRM)
     np.testing.assert_allclose(a.loglik_terms(), (slog, squad), rtol=1e-10)
+
+
+@pytest.mark.parametrize("n,D,m,kernel_id", [(1500, 2, 10, 1), (700, 3, 6, 0), (400, 1, 4, 0), (600, 2, 5, 2)])
+def test_latent_density(n, D, m, kernel_id):
+    """loglik_latent: reference rows without a nugget, observation rows with tau2 + eps^2 through nngp_set_eps2
+    (the records' z slot for D < 3, its own array for D = 3)."""
+    t, y = synthetic(n, D, 31 + D)
+    hc.check_latent_density(make_with(SPECS[kernel_id]), t, y, m, kernel_id, PRM)
+
+
+def test_latent_density_dense_identity():
+    t, y = synthetic(20, 2, 33)
+    for kid in (0, 1):
+        hc.check_latent_dense_identity(make_with(SPECS[kid]), t, y, kid, PRM)

@@ -156,3 +156,15 @@ def test_random_reference_set(make):
     hc.check_random(lambda *a, **k: make(*a, Matern(1.5), **k), t, y, 70, 6, 1, PRM)
     t3, y3 = synthetic(120, 3, 13)
     hc.check_random(lambda *a, **k: make(*a, Exponential(), **k), t3, y3, 40, 4, 0, PRM)
+
+
+def test_latent_density(make):
+    t, y = synthetic(150, 2, 31)
+    hc.check_latent_density(lambda *a, **k: make(*a, Matern(1.5), **k), t, y, 6, 1, PRM)
+    t1, y1 = synthetic(90, 1, 32)
+    hc.check_latent_density(lambda *a, **k: make(*a, Exponential(), **k), t1, y1, 4, 0, PRM)
+
+
+def test_latent_density_dense_identity(make):
+    t, y = synthetic(20, 2, 33)
+    hc.check_latent_dense_identity(lambda *a, **k: make(*a, Exponential(), **k), t, y, 0, PRM)
