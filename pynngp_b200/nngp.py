@@ -611,6 +611,21 @@ class NNGP(object):
             chain[k], trace[k] = theta, cur
         return chain, trace, acc / max(n_steps, 1)
 
+    def close(self):
+        """Releases the device memory of this object's engines (also done when the object is collected)."""
+        for name in ("_latent_eng", "_engine"):
+            eng = getattr(self, name, None)
+            if eng is not None:
+                eng.close()
+        self._latent_eng = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+        return False
+
     def oneSample(self):
         # nngp.py:98-101 calls update_wt / update_ws / update_y_unobserved, none of which exist upstream
         raise NotImplementedError("the reference's Gibbs sweep is unimplemented upstream (nngp.py:98-101)")

@@ -168,3 +168,12 @@ def test_latent_density(make):
 def test_latent_density_dense_identity(make):
     t, y = synthetic(20, 2, 33)
     hc.check_latent_dense_identity(lambda *a, **k: make(*a, Exponential(), **k), t, y, 0, PRM)
+
+
+def test_close_releases_both_engines(make):
+    t, y = synthetic(60, 2, 3)
+    with make(t, y, 0.0, "S=T", 4, Exponential(*PRM)) as obj:
+        obj.loglik_latent(y)
+        main, latent = obj._engine, obj._latent_eng
+        assert not main._closed and not latent._closed
+    assert main._closed and latent._closed and obj._latent_eng is None
