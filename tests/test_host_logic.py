@@ -177,3 +177,60 @@ def test_close_releases_both_engines(make):
         main, latent = obj._engine, obj._latent_eng
         assert not main._closed and not latent._closed
     assert main._closed and latent._closed and obj._latent_eng is None
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_random_configurations_hold_the_invariants(make, seed):
+    """Seeded sweep over (n, D, m, refType, response columns, eps form): whatever the shapes -- m >= n, n below the
+    5 neighbours `ws` asks for, a subset of everything, 1-D sites given as a flat array -- the likelihood equals the
+    oracle's on the engine's row layout and the reference's attributes keep their shapes."""
+    rng = np.random.default_rng(1000 + seed)
+    n = int(rng.integers(2, 70))
+    D = int(rng.integers(1, 4))
+    m = int(rng.integers(1, 13))
+    ncol = int(rng.integers(1, 3))
+    kid = int(rng.integers(0, 3))
+    spec = [Exponential(*PRM), Matern(1.5, *PRM), Matern(2.5, *PRM)][kid]
+    t = rng.random((n, D))
+    t_arg = t[:, 0] if D == 1 and seed % 2 else t           # flat 1-D sites, as the reference would accept them
+    y = rng.standard_normal((n, ncol)) if ncol > 1 else rng.standard_normal(n)
+    eps = [0.0, 0.15, np.abs(rng.standard_normal(np.shape(y))) * 0.2][seed % 3]
+    kind = ["S=T", "subset", "random"][int(rng.integers(0, 3))]
+    if kind == "S=T":
+        ref = "S=T"
+    else:
+        n_ref = int(rng.integers(1, n + 1))
+        if m > n_ref:
+            with pytest.raises(ValueError):
+                make(t_arg, y, eps, (kind, n_ref) + (((0, 1),) * D,) * (kind == "random"), m, spec, seed=seed)
+            return
+        ref = ("subset", n_ref) if kind == "subset" else ("random", n_ref, ((0.0, 1.0),) * D)
+    obj = make(t_arg, y, eps, ref, m, spec, seed=seed)
+    n_ref = obj._n_ref
+    assert len(obj.Ns) == n_ref and obj.Ns[0] == [] and len(obj.Nt) == (n_ref if kind == "S=T" else n)
+    assert all(len(obj.Ns[i]) == min(m, i) for i in range(n_ref))
+    assert np.shape(obj.ws) == (n_ref,) + np.shape(y)[1:] and np.array_equal(obj.wt, y)
+    if kind != "S=T":
+        d, idx = obj.Nt[n - 1]
+        assert d.shape == idx.shape == (1, m) and (np.diff(d[0]) >= 0).all() and (idx < n_ref).all()
+    y2d = np.asarray(y, dtype=np.float64).reshape(n, -1)
+    e2 = np.broadcast_to(np.asarray(eps, dtype=np.float64).reshape((n, -1) if np.ndim(eps) else (1, 1)), y2d.shape) ** 2
+    if kind == "random":
+        with pytest.raises(NotImplementedError):
+            obj.loglik()
+    else:
+        rows = np.arange(n) if obj._rows is None else obj._rows
+        want = np.zeros(3)
+        for c in range(ncol):
+            want += orc.c_loglik(t[rows], y2d[rows, c], obj._table, kid, *PRM, eps2=e2[rows, c] if np.any(e2) else None)
+        got = obj.loglik_batch([PRM])[0]
+        np.testing.assert_allclose(got, want, rtol=1e-11)
+        mean, var = obj.predict(rng.random((3, D)), m=min(m, n_ref))
+        assert mean.shape == var.shape == (3,) + np.shape(y)[1:] and (var > 0).all()
+    w = rng.standard_normal((n_ref, ncol))
+    ll = obj.loglik_latent(w if ncol > 1 else w[:, 0])
+    want_ll = 0.0
+    for c in range(ncol):
+        want_ll += hc._latent_expected(np.asarray(obj.s, dtype=np.float64).reshape(n_ref, -1), w[:, c], t, y2d[:, c],
+                                       m, kid, PRM, eps2_t=e2[:, c] if np.any(e2) else None)
+    np.testing.assert_allclose(ll, want_ll, rtol=1e-7)
