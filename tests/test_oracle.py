@@ -235,3 +235,35 @@ def test_grid_search_model_random_sweep():
         want = orc.c_knn_ordered(s, m)
         got = gm.grid_knn_ordered(s, m, lam_scale=float(rng.choice([0.2, 1.0, 3.0])), brute_rows=128)
         assert np.array_equal(got, want), (D, n, m)
+
+
+@pytest.mark.parametrize("kernel_id,D,m", [(0, 2, 5), (1, 2, 7), (2, 3, 4), (1, 1, 3)])
+def test_loglik_equals_product_of_gaussian_conditionals_scipy(kernel_id, D, m):
+    """Independent known answer for m < n - 1 (the dense-GP identity only covers m = n - 1): by definition the
+    NNGP density is prod_i p(y_i | y_N(i)) under the parent GP, and each factor is a ratio of two multivariate
+    normal densities, log N([y_N, y_i]; 0, C_joint) - log N(y_N; 0, C_N).  SciPy's multivariate_normal (an
+    eigendecomposition, not a Cholesky/LDL^T elimination) evaluates both; the oracle's sum of
+    log F_i + r_i^2 / F_i must give the same number.  Covers per-observation eps as well."""
+    from scipy.stats import multivariate_normal
+
+    n = 70
+    s, y = synthetic(n, D, 50 + kernel_id)
+    rng = np.random.default_rng(kernel_id)
+    eps2 = rng.random(n) * 0.05
+    sigma2, phi, tau2 = 1.3, 4.0, 0.09
+    tab = orc.c_knn_ordered(s, m)
+    d = np.sqrt(((s[:, None, :] - s[None, :, :]) ** 2).sum(-1))
+    C = sigma2 * orc.np_corr(kernel_id, phi * d)
+    C[np.diag_indices(n)] = sigma2 + tau2 + eps2
+    want = 0.0
+    for i in range(n):
+        N = tab[i][tab[i] >= 0]
+        idx = np.concatenate([N, [i]])
+        want += multivariate_normal(np.zeros(len(idx)), C[np.ix_(idx, idx)], allow_singular=False).logpdf(y[idx])
+        if len(N):
+            want -= multivariate_normal(np.zeros(len(N)), C[np.ix_(N, N)], allow_singular=False).logpdf(y[N])
+    slog, squad, bad = orc.c_loglik(s, y, tab, kernel_id, sigma2, phi, tau2, eps2=eps2)
+    assert bad == 0
+    np.testing.assert_allclose(orc.loglik_from_terms(slog, squad, n), want, rtol=1e-10)
+    npo = orc.NumpyNNGP(s, y, tab, kernel_id, sigma2, phi, tau2, eps2=eps2)
+    np.testing.assert_allclose(orc.loglik_from_terms(*npo.loglik_terms(), n), want, rtol=1e-10)
