@@ -14,7 +14,8 @@ Two restatements of the same algorithm live here:
 Pinning: stage 1 (neighbour sets) is pinned bit-exactly to the unmodified reference through
 ``tests/golden/ns_*.npz`` (made by ``tests/golden/make_golden.py``, which imports /root/reference).
 Stages 2-3 (C_N, c, b, F, log-likelihood) are PARITY UNPINNED by the reference -- ``nngp.py:73-96``
-are empty stubs with no test vectors -- and are anchored to the dense-GP identity and closed forms.
+are empty stubs with no test vectors -- and are anchored to the dense-GP identity, to the product of the
+parent GP's conditionals evaluated by SciPy's multivariate normal (m < n - 1), and to closed forms.
 """
 from __future__ import annotations
 
