@@ -8,14 +8,22 @@
  * Conventions
  *   - every function returns 0 on success and a nonzero NNGP_E* code on failure; the message is
  *     available from nngp_last_error(h) (or nngp_last_error(NULL) for a failed nngp_create).
- *   - one handle = one CUDA device = one shard of the ordering (rows [lo, hi) of the location
- *     list).  Multi-GPU runs use one process (and one handle) per GPU; the cross-GPU sum of the
- *     3*K partial statistics is the caller's allreduce (NCCL through torch.distributed in
- *     pynngp_b200/dist.py).
+ *   - a device handle (nngp_create) = one CUDA device = one shard of the ordering (rows [lo, hi) of the
+ *     location list).  Multi-GPU, two ways:
+ *       (a) one process per GPU, one device handle each; the sum of the 3*K partial statistics over the
+ *           ranks is fused into the kernel's tail over NVLink peer memory (nngp_peer_export /
+ *           nngp_peer_connect / nngp_loglik_allreduce), or left to the caller's allreduce;
+ *       (b) ONE process, a multi-device handle (nngp_create_multi): the same entry points fan out over
+ *           one sub-handle and one launcher thread per device, the shard is split evenly over the
+ *           devices, and nngp_loglik returns the total -- what a plain caller of the reference's
+ *           constructor (pyNNGP/nngp.py:6) gets without torchrun.
  *   - the caller owns every host buffer; the library copies in / out and never keeps host
  *     pointers.  The handle owns device memory and its stream.
- *   - plain-pointer calls are synchronous on return.  *_device calls take device pointers and a
- *     cudaStream_t (as void*), are asynchronous, and are what an on-device sweep/MCMC loop uses.
+ *   - plain-pointer calls are synchronous on return.  Evaluations carry up to 8 parameter vectors
+ *     in the kernel arguments and receive the statistics through mapped pinned host memory that the
+ *     kernel's last block writes and the calling thread polls: no H2D / D2H copy, no stream sync.
+ *     *_device calls take device pointers and a cudaStream_t (as void*), are asynchronous, and are
+ *     what an on-device sweep/MCMC loop uses.
  *   - a handle is not thread-safe; distinct handles are independent.
  *   - there is NO CPU fallback: without a CUDA device nngp_create fails with NNGP_ENODEVICE.
  */
@@ -53,6 +61,15 @@ const char *nngp_last_error(const nngp_handle *h);
 /* Creates an engine on CUDA device `device` computing stages 2-3 in `dtype` (NNGP_F64|NNGP_F32;
  * stage 1 is always fp64).  Replaces: object construction, nngp.py:6-12. */
 int nngp_create(nngp_handle **h, int device, int dtype);
+/* One handle over `ndev` (1..8) distinct devices of this process (nngp_create(h, devices, ndev,
+ * dtype)).  The devices must have P2P access to each other (one NVLink / NVSwitch domain).  Every entry point
+ * below accepts it unless it says otherwise: data is replicated, the shard and the neighbour table are split in
+ * contiguous blocks over the devices, evaluations return the total.  Device-pointer entry points
+ * (nngp_loglik_device*, nngp_peer_*, nngp_neighbors_device_ptr) and nngp_build_neighbors /
+ * nngp_build_neighbors_capped are for device handles only (NNGP_ESTATE). */
+int nngp_create_multi(nngp_handle **h, const int *devices, int ndev, int dtype);
+int nngp_device_count(const nngp_handle *h);  /* devices behind this handle */
+int nngp_visible_devices(void);               /* sm_100 devices this process can see (0 without a driver) */
 void nngp_destroy(nngp_handle *h);
 
 /* Uploads the reference set and the response.  coords: n x D row-major fp64 (the reference's
@@ -89,6 +106,12 @@ int nngp_build_neighbors(nngp_handle *h, int m, int tile_offset, int tile_stride
  * histogram predicts more work than brute force; NNGP_KNN_GRID / NNGP_KNN_BRUTE force one. */
 enum { NNGP_KNN_AUTO = 0, NNGP_KNN_GRID = 1, NNGP_KNN_BRUTE = 2 };
 int nngp_build_neighbors_grid(nngp_handle *h, int m, int64_t row_lo, int64_t row_hi, int algo);
+/* The same search for the rows of the handle's shard [lo, hi) ONLY, and the table keeps only those rows
+ * ((hi - lo) x m instead of n x m: what a rank of a multi-GPU run needs -- SURVEY 8 e2).  Evaluations,
+ * nngp_factors, nngp_cov_blocks and nngp_get_neighbor_rows then work on rows inside that window;
+ * nngp_get_neighbors needs a full table.  nngp_neighbor_window reports the rows held. */
+int nngp_build_neighbors_shard(nngp_handle *h, int m, int algo);
+int nngp_neighbor_window(const nngp_handle *h, int64_t *row0, int64_t *rows);
 /* Same search with the candidates of row i restricted to j < min(i, cand_cap).  Replaces
  * _make_t_neighbor_sets for S != T, nngp.py:68-71 (KDTree(s).query(t_i, m): the sites of t appended after
  * the nRef rows of s, row_lo = cand_cap = nRef).  With the n reference
@@ -101,7 +124,9 @@ int nngp_build_neighbors_capped(nngp_handle *h, int m, int64_t row_lo, int64_t r
 int nngp_set_knn_tuning(nngp_handle *h, double lambda_scale, int64_t brute_rows);
 /* 1 if the last nngp_build_neighbors_grid call went through the grid, 0 if it fell back. */
 int nngp_knn_used_grid(const nngp_handle *h);
-/* Injects a table (n x m int32 row-major, -1 padded; valid entries first in each row). */
+/* Injects a table (n x m int32 row-major, -1 padded; valid entries first in each row).  The table is checked on
+ * the device before it is accepted: every entry of row i must lie in [-1, i) -- neighbours precede their row, so no
+ * gather can leave the records -- with the padding at the tail; otherwise NNGP_EINVAL. */
 int nngp_set_neighbors(nngp_handle *h, const int32_t *idx, int m);
 int nngp_get_neighbors(nngp_handle *h, int32_t *out);
 /* Rows [i0, i1) of the table only: out is (i1-i0) x m int32. */
@@ -110,8 +135,10 @@ int nngp_get_neighbor_rows(nngp_handle *h, int64_t i0, int64_t i1, int32_t *out)
  * out: n x k int32 on the host.  Replaces the neighbour search inside _init_ws, nngp.py:45-47
  * (KNeighborsRegressor(5).fit(t, y).predict(s): the mean of y over these rows is `ws`). */
 int nngp_knn_plain(nngp_handle *h, int k, int32_t *out);
-/* Device address of the n x m int32 table (for an NCCL exchange by the caller), or NULL. */
+/* Device address of the n x m int32 table (for an NCCL exchange by the caller), or NULL when the handle holds
+ * a window only; nngp_neighbor_window_device_ptr is the address of the first row HELD (see nngp_neighbor_window). */
 void *nngp_neighbors_device_ptr(nngp_handle *h);
+void *nngp_neighbor_window_device_ptr(nngp_handle *h);
 
 /* Stages 2-3 fused -- the metric's call.  For each of K parameter vectors
  * (params: K x NNGP_NPARAM fp64) builds C_N(i), c_i, C(i,i) (_CNs nngp.py:78-82, _Ccross
@@ -120,6 +147,11 @@ void *nngp_neighbors_device_ptr(nngp_handle *h);
  * n_bad}; locations whose factorisation met a non-positive pivot are counted in n_bad and left out
  * of the sums. */
 int nngp_loglik(nngp_handle *h, int kernel_id, const double *params, int K, double *out);
+/* One parameter vector by value: out3 = {sum log F_i, sum r_i^2/F_i, n_bad}.  The shortest host path of the
+ * metric's call (an MCMC step): no staging buffers, no copies.  The result is the total over all GPUs when the
+ * handle is a multi-device handle or its peer exchange is connected (every rank must then call it), otherwise
+ * the handle's shard. */
+int nngp_loglik_terms(nngp_handle *h, int kernel_id, double sigma2, double phi, double tau2, double *out3);
 /* Same with device pointers on `stream` (NULL = the handle's stream); no host synchronisation. */
 int nngp_loglik_device(nngp_handle *h, int kernel_id, const double *d_params, int K,
                        double *d_out, void *stream);
@@ -130,9 +162,10 @@ int nngp_loglik_device(nngp_handle *h, int kernel_id, const double *d_params, in
  * rank order (any transport; pynngp_b200 uses torch.distributed), and every rank calls nngp_peer_connect.
  * nngp_loglik_device_allreduce then behaves like nngp_loglik_device except that d_out receives the sum over
  * ALL ranks, bitwise identical on every rank: the last block of each rank stores its K x 3 partials into
- * every peer's buffer over NVLink (P2P stores), flags them, waits for all ranks' flags and sums in rank
- * order -- no second launch, no NCCL call.  Every rank must issue the same sequence of these calls.  If a
- * peer does not arrive within ~30 s the statistics come back as NaN. */
+ * every peer's buffer over NVLink (P2P stores of self-stamped 16-byte lines: no flag, no fence), waits for all
+ * ranks' lines and sums in rank order -- no second launch, no NCCL call.  Every rank must issue the same
+ * sequence of these calls.  If a peer does not arrive within ~30 s the statistics come back as NaN.
+ * K_cap must not exceed the device's SM count (one waiting block per parameter vector must stay resident). */
 #define NNGP_IPC_HANDLE_BYTES 64
 int nngp_peer_export(nngp_handle *h, int K_cap, unsigned char *handle_out);
 int nngp_peer_connect(nngp_handle *h, int rank, int world, const unsigned char *handles);

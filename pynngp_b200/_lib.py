@@ -29,6 +29,9 @@ SIGNATURES = {
     "nngp_version": (ctypes.c_char_p, []),
     "nngp_last_error": (ctypes.c_char_p, [_handle_p]),
     "nngp_create": (ctypes.c_int, [ctypes.POINTER(_handle_p), ctypes.c_int, ctypes.c_int]),
+    "nngp_create_multi": (ctypes.c_int, [ctypes.POINTER(_handle_p), ctypes.POINTER(ctypes.c_int), ctypes.c_int, ctypes.c_int]),
+    "nngp_device_count": (ctypes.c_int, [_handle_p]),
+    "nngp_visible_devices": (ctypes.c_int, []),
     "nngp_destroy": (None, [_handle_p]),
     "nngp_set_data": (ctypes.c_int, [_handle_p, _c_double_p, ctypes.c_int64, ctypes.c_int, _c_double_p, _c_double_p]),
     "nngp_set_y": (ctypes.c_int, [_handle_p, _c_double_p]),
@@ -36,6 +39,8 @@ SIGNATURES = {
     "nngp_set_shard": (ctypes.c_int, [_handle_p, ctypes.c_int64, ctypes.c_int64]),
     "nngp_build_neighbors": (ctypes.c_int, [_handle_p, ctypes.c_int, ctypes.c_int, ctypes.c_int]),
     "nngp_build_neighbors_grid": (ctypes.c_int, [_handle_p, ctypes.c_int, ctypes.c_int64, ctypes.c_int64, ctypes.c_int]),
+    "nngp_build_neighbors_shard": (ctypes.c_int, [_handle_p, ctypes.c_int, ctypes.c_int]),
+    "nngp_neighbor_window": (ctypes.c_int, [_handle_p, ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ctypes.c_int64)]),
     "nngp_build_neighbors_capped": (ctypes.c_int, [_handle_p, ctypes.c_int, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, ctypes.c_int]),
     "nngp_set_knn_tuning": (ctypes.c_int, [_handle_p, ctypes.c_double, ctypes.c_int64]),
     "nngp_knn_used_grid": (ctypes.c_int, [_handle_p]),
@@ -44,6 +49,8 @@ SIGNATURES = {
     "nngp_get_neighbor_rows": (ctypes.c_int, [_handle_p, ctypes.c_int64, ctypes.c_int64, _c_int32_p]),
     "nngp_knn_plain": (ctypes.c_int, [_handle_p, ctypes.c_int, _c_int32_p]),
     "nngp_neighbors_device_ptr": (ctypes.c_void_p, [_handle_p]),
+    "nngp_neighbor_window_device_ptr": (ctypes.c_void_p, [_handle_p]),
+    "nngp_loglik_terms": (ctypes.c_int, [_handle_p, ctypes.c_int, ctypes.c_double, ctypes.c_double, ctypes.c_double, _c_double_p]),
     "nngp_loglik": (ctypes.c_int, [_handle_p, ctypes.c_int, _c_double_p, ctypes.c_int, _c_double_p]),
     "nngp_loglik_device": (ctypes.c_int, [_handle_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]),
     "nngp_peer_export": (ctypes.c_int, [_handle_p, ctypes.c_int, ctypes.c_char_p]),
@@ -80,6 +87,11 @@ def load():
     return _lib
 
 
+def device_count():
+    """Number of CUDA devices this process can see (0 without a driver); no engine is created."""
+    return int(load().nngp_visible_devices())
+
+
 def _dp(a):
     return None if a is None else a.ctypes.data_as(_c_double_p)
 
@@ -92,7 +104,9 @@ def _f64(a, shape=None):
 
 
 class Engine:
-    """One handle = one GPU = one shard of the ordering.  Thin, 1:1 over the C ABI."""
+    """One handle = one GPU = one shard of the ordering (``device`` an int), or one multi-device handle
+    (``device`` a list of device indices: nngp_create_multi -- data replicated, shard and table split over
+    the devices, evaluations return the total).  Thin, 1:1 over the C ABI."""
 
     def __init__(self, device=0, dtype="float64"):
         self._lib = load()
@@ -100,13 +114,25 @@ class Engine:
         code = {"float64": F64, "float32": F32}.get(str(dtype))
         if code is None:
             raise ValueError("dtype must be 'float64' or 'float32'")
-        rc = self._lib.nngp_create(ctypes.byref(self._h), int(device), code)
+        if isinstance(device, (list, tuple)):
+            devs = [int(d) for d in device]
+            arr = (ctypes.c_int * len(devs))(*devs)
+            rc = self._lib.nngp_create_multi(ctypes.byref(self._h), arr, len(devs), code)
+            what = "nngp_create_multi"
+            self.devices, self.device = devs, (devs[0] if devs else 0)
+        else:
+            rc = self._lib.nngp_create(ctypes.byref(self._h), int(device), code)
+            what = "nngp_create"
+            self.devices, self.device = [int(device)], int(device)
         if rc != 0:
             msg = self._lib.nngp_last_error(None).decode()
             self._h = None
-            raise NNGPError(f"nngp_create failed ({rc}): {msg}")
-        self.device, self.dtype = int(device), str(dtype)
+            raise NNGPError(f"{what} failed ({rc}): {msg}")
+        self.dtype = str(dtype)
         self.n = self.D = self.m = 0
+        # preallocated argument / result storage of the one-vector fast path (loglik_terms)
+        self._out3 = (ctypes.c_double * NSTAT)()
+        self._terms = self._lib.nngp_loglik_terms
 
     def _check(self, rc, what):
         if rc != 0:
@@ -160,6 +186,18 @@ class Engine:
                     "nngp_build_neighbors_grid")
         self.m = int(m)
 
+    def build_neighbors_shard(self, m, algo="auto"):
+        """Stage 1 for the rows of the handle's shard only; the table keeps only those rows."""
+        code = {"auto": 0, "grid": 1, "brute": 2}[algo]
+        self._check(self._lib.nngp_build_neighbors_shard(self._h, int(m), code), "nngp_build_neighbors_shard")
+        self.m = int(m)
+
+    def neighbor_window(self):
+        """(row0, rows): the rows of the n x m table this handle holds."""
+        a, b = ctypes.c_int64(0), ctypes.c_int64(0)
+        self._check(self._lib.nngp_neighbor_window(self._h, ctypes.byref(a), ctypes.byref(b)), "nngp_neighbor_window")
+        return a.value, b.value
+
     def build_neighbors_capped(self, m, row_lo, row_hi, cand_cap, algo="auto"):
         """Rows [row_lo, row_hi): the m nearest j < min(i, cand_cap) (prediction sites appended after the
         cand_cap reference sites get reference-only neighbours)."""
@@ -202,6 +240,9 @@ class Engine:
     def neighbors_device_ptr(self):
         return self._lib.nngp_neighbors_device_ptr(self._h)
 
+    def neighbor_window_device_ptr(self):
+        return self._lib.nngp_neighbor_window_device_ptr(self._h)
+
     # -- stages 2-3 --------------------------------------------------------------------------------
     def loglik(self, kernel_id, params):
         """params (K, 4) -> stats (K, 3) = [sum log F, sum r^2/F, n_bad] over the shard."""
@@ -214,6 +255,15 @@ class Engine:
         self._check(self._lib.nngp_loglik(self._h, int(kernel_id), _dp(params), params.shape[0], _dp(out)),
                     "nngp_loglik")
         return out
+
+    def loglik_terms(self, kernel_id, sigma2, phi, tau2):
+        """One parameter vector by value -> (sum log F, sum r^2/F, n_bad); the total over all GPUs for a
+        multi-device handle or a connected peer exchange.  No array is allocated on this path."""
+        rc = self._terms(self._h, kernel_id, sigma2, phi, tau2, self._out3)
+        if rc != 0:
+            self._check(rc, "nngp_loglik_terms")
+        o = self._out3
+        return o[0], o[1], o[2]
 
     def loglik_allreduce(self, kernel_id, params):
         """Like loglik, but the (K, 3) result is the total over all ranks (fused peer-memory exchange)."""

@@ -49,12 +49,17 @@ def _stale(target, deps):
     return any(os.path.getmtime(d) > t for d in deps)
 
 
+def _dev_defines():
+    """Development-only preprocessor defines (NNGP_DEV_DEFINES="NNGP_TUNE,NNGP_TIMELINE"); empty for the product."""
+    return [f"-D{d.strip()}=1" for d in os.environ.get("NNGP_DEV_DEFINES", "").split(",") if d.strip()]
+
+
 def _compile(src, verbose):
     obj = os.path.join(OBJ_DIR, src.replace(".cu", ".o"))
     path = os.path.join(CSRC, src)
     if not _stale(obj, [path] + _deps()):
         return obj, ""
-    cmd = [_nvcc(), *NVCC_FLAGS, "-c", path, "-o", obj]
+    cmd = [_nvcc(), *NVCC_FLAGS, *_dev_defines(), "-c", path, "-o", obj]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"nvcc failed on {src}:\n{r.stdout}\n{r.stderr}")

@@ -1,7 +1,8 @@
 // fused_f64_m32.cu -- instantiates the fused covariance/factorisation/reduction kernel
 // (loglik_fused.cuh) for arithmetic type double and correlation family NNGP_MATERN32.
-#define NNGP_TUNE 1
-// #define NNGP_TIMELINE 1   // development: per-phase / per-block globaltimer stamps (tools/timeline*.py)
+// Development builds only (never the shipped library): `NNGP_DEV_DEFINES="NNGP_TUNE" python -m pynngp_b200.build --force`
+// compiles the shape knobs tools/tune.py drives through NNGP_TUNE_SHAPE; NNGP_TIMELINE adds per-phase / per-block
+// globaltimer stamps (tools/timeline*.py).  Without those defines the dispatch reads no environment variable.
 #include "loglik_fused.cuh"
 
 NNGP_DEFINE_FAMILY(f64_m32, double, NNGP_MATERN32)

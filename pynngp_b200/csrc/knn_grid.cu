@@ -330,15 +330,12 @@ GridSpec make_grid(const nngp_handle *h, double nref, double lambda, int64_t max
 
 inline size_t query_smem(int m) { return size_t(m) * TQ * (sizeof(double) + sizeof(int32_t)); }
 
+// handle-owned (scratch_get): a build costs no cudaMalloc / cudaFree after the first one
 struct Scratch {
     double4 *sorted = nullptr;
     int *cell_of = nullptr, *qlist = nullptr;
     int *cells = nullptr;  // 6 arrays of (cap_cells + 1)
     double *sumsq = nullptr;
-    ~Scratch()
-    {
-        cudaFree(sorted); cudaFree(cell_of); cudaFree(qlist); cudaFree(cells); cudaFree(sumsq);
-    }
 };
 
 }  // namespace nngp_grid
@@ -356,7 +353,7 @@ cudaError_t launch_fill_i32(nngp_handle *h, int32_t *p, int64_t count, int32_t v
 // included.  *used = 0 (and nothing computed) when the data does not suit a grid and force == 0:
 // non-finite coordinates, or a histogram that predicts more work than brute force.
 cudaError_t launch_knn_grid(nngp_handle *h, bool ordered, int m, int64_t row_lo, int64_t row_hi, int64_t cand_cap,
-                            int32_t *table, cudaStream_t stream, int force, int *used)
+                            int32_t *table, bool window, cudaStream_t stream, int force, int *used)
 {
     using namespace nngp_grid;
     *used = 0;
@@ -405,7 +402,7 @@ cudaError_t launch_knn_grid(nngp_handle *h, bool ordered, int m, int64_t row_lo,
                          : (dim3 ? knn_grid_query_kernel<true, false> : knn_grid_query_kernel<false, false>);
     const size_t smem = query_smem(m);
     GRID_TRY(cudaFuncSetAttribute(qkern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const bool partial = row_lo > 0 || row_hi < n;
+    const bool partial = !window && (row_lo > 0 || row_hi < n);  // a window table has no rows outside [row_lo, row_hi)
     bool filled = false;
 
     // Clustered data: when the top level's histogram predicts too much work, the cells are refined (a
@@ -419,11 +416,11 @@ cudaError_t launch_knn_grid(nngp_handle *h, bool ordered, int m, int64_t row_lo,
     if (any_level) {
         for (int l = 0; l < nlev; ++l)
             cap_cells = std::max(cap_cells, make_grid(h, double(ordered ? std::min(lev[l].a, cand_cap) : n), lam_use, max_cells).ncell);
-        GRID_TRY(cudaMalloc(&sc.sorted, sizeof(double4) * size_t(n)));
-        GRID_TRY(cudaMalloc(&sc.cell_of, sizeof(int) * size_t(n)));
-        GRID_TRY(cudaMalloc(&sc.qlist, sizeof(int) * size_t(n)));
-        GRID_TRY(cudaMalloc(&sc.cells, sizeof(int) * 6 * size_t(cap_cells + 1)));
-        GRID_TRY(cudaMalloc(&sc.sumsq, sizeof(double)));
+        GRID_TRY(scratch_get(h, 0, sizeof(double4) * size_t(n), reinterpret_cast<void **>(&sc.sorted)));
+        GRID_TRY(scratch_get(h, 1, sizeof(int) * size_t(n), reinterpret_cast<void **>(&sc.cell_of)));
+        GRID_TRY(scratch_get(h, 2, sizeof(int) * size_t(n), reinterpret_cast<void **>(&sc.qlist)));
+        GRID_TRY(scratch_get(h, 3, sizeof(int) * 6 * size_t(cap_cells + 1), reinterpret_cast<void **>(&sc.cells)));
+        GRID_TRY(scratch_get(h, 4, sizeof(double), reinterpret_cast<void **>(&sc.sumsq)));
     }
     int *counts = sc.cells, *starts = counts + (cap_cells + 1), *cursor = starts + (cap_cells + 1);
     int *qcounts = cursor + (cap_cells + 1), *qstarts = qcounts + (cap_cells + 1), *qcursor = qstarts + (cap_cells + 1);
@@ -481,8 +478,9 @@ cudaError_t launch_knn_grid(nngp_handle *h, bool ordered, int m, int64_t row_lo,
         GRID_TRY(cudaGetLastError());
         ++h->launches;
     }
-    if (ordered && row_lo < T0 && T0 > 0) GRID_TRY(launch_knn_brute_rows(h, m, 0, T0, cand_cap, table, stream));
-    GRID_TRY(cudaStreamSynchronize(stream));  // scratch is freed on return
+    if (ordered && row_lo < T0 && T0 > 0)
+        GRID_TRY(launch_knn_brute_rows(h, m, row_lo, std::min(T0, row_hi), cand_cap, table, stream));
+    GRID_TRY(cudaStreamSynchronize(stream));
 #undef GRID_TRY
     *used = 1;
     return cudaSuccess;
@@ -490,20 +488,19 @@ cudaError_t launch_knn_grid(nngp_handle *h, bool ordered, int m, int64_t row_lo,
 
 // A rank with an empty shard still takes part in the statistics exchange: one block per parameter vector
 // publishes zeros and collects the sum (peer_exchange.cuh).
-__global__ void __launch_bounds__(32) peer_zero_kernel(PeerExchange px, double *out)
+__global__ void __launch_bounds__(32) peer_zero_kernel(PeerExchange px, EvalArgs a)
 {
-    __shared__ double sh[16];
+    __shared__ double sh[3 + 2 * 24];
     double tot[3] = {0.0, 0.0, 0.0};
-    peer_allreduce3(px, blockIdx.x, 0.0, 0.0, 0.0, sh, tot);
-    if (threadIdx.x == 0) {
-        out[size_t(blockIdx.x) * 3 + 0] = tot[0];
-        out[size_t(blockIdx.x) * 3 + 1] = tot[1];
-        out[size_t(blockIdx.x) * 3 + 2] = tot[2];
-    }
+    if (px.world > 1) peer_allreduce3(px, blockIdx.x, 0.0, 0.0, 0.0, sh, tot);
+    if (threadIdx.x == 0) publish_result(a, blockIdx.x, tot);
 }
 
-cudaError_t launch_peer_zero(nngp_handle *, const PeerExchange &px, int K, double *d_out, cudaStream_t stream)
+cudaError_t launch_peer_zero(nngp_handle *, const PeerExchange &px, int K, double *d_out, uint4 *hout, unsigned int seq,
+                             cudaStream_t stream)
 {
-    peer_zero_kernel<<<K, 32, 0, stream>>>(px, d_out);
+    EvalArgs a{};
+    a.out = d_out; a.hout = hout; a.seq = seq;
+    peer_zero_kernel<<<K, 32, 0, stream>>>(px, a);
     return cudaGetLastError();
 }

@@ -112,7 +112,7 @@ __device__ __forceinline__ double dist2_sk(double qx, double qy, double qz, cons
 template <bool DIM3, bool ORDERED>
 __global__ void __launch_bounds__(TQ) knn_ordered_kernel(const double4 *__restrict__ pts, int64_t n,
                                                          int m, int ntiles, int tile_offset,
-                                                         int tile_stride, int first_tile, int64_t cand_cap,
+                                                         int tile_stride, int first_tile, int64_t out_lo, int64_t cand_cap,
                                                          unsigned int *tile_counter,
                                                          int32_t *__restrict__ out)
 {
@@ -210,7 +210,7 @@ __global__ void __launch_bounds__(TQ) knn_ordered_kernel(const double4 *__restri
             if (tid == 0 && c + NSTAGE < nct) issue(c + NSTAGE);
         }
 
-        if (live) {
+        if (live && i >= out_lo) {  // rows below out_lo share the first tile but are not wanted (and may not exist)
             int32_t *row = out + i * m;
             for (int k = 0; k < m; ++k) row[k] = k < top.cnt ? top.ids[k * TQ] : -1;
         }
@@ -258,7 +258,7 @@ static cudaError_t launch_knn(nngp_handle *h, bool ordered, int m, int tile_offs
     const int my_tiles = (ntiles - first_tile - tile_offset + tile_stride - 1) / tile_stride;
     int grid = h->num_sms * per_sm;
     if (grid > my_tiles) grid = my_tiles > 0 ? my_tiles : 1;
-    kern<<<grid, TQ, smem, stream>>>(h->pts, n, m, ntiles, tile_offset, tile_stride, first_tile, cand_cap,
+    kern<<<grid, TQ, smem, stream>>>(h->pts, n, m, ntiles, tile_offset, tile_stride, first_tile, first_row, cand_cap,
                                      h->d_tile_counter, table);
     ++h->launches;
     return cudaGetLastError();

@@ -386,7 +386,7 @@ template <> struct Pair2<float> { using type = float2; };
 // EMIT: the variant that also writes per-location outputs (accessors, factors(), prediction); compiled
 // separately so the metric's kernel carries none of its code or registers.
 template <typename T, int G, int R, int KERN, bool DIM3, int MINB, int BUILD, int ELIM, bool EMIT>
-__global__ void __launch_bounds__(kThreads, MINB) fused_loglik_kernel(const EvalArgs a)
+__global__ void __launch_bounds__(kThreads, MINB) fused_loglik_kernel(const __grid_constant__ EvalArgs a)
 {
     constexpr int P = G * R;   // rows of the augmented matrix
     constexpr int W = 32 / G;  // locations per warp
@@ -429,15 +429,18 @@ __global__ void __launch_bounds__(kThreads, MINB) fused_loglik_kernel(const Eval
     // sweep: blockIdx.y = chunk of parameter vectors [k0, k0 + kc); otherwise one vector per blockIdx.y
     const int k0 = SWEEP ? int(blockIdx.y) * kSweepChunk : int(blockIdx.y);
     const int kc = SWEEP ? (a.K - k0 < kSweepChunk ? a.K - k0 : kSweepChunk) : 1;
-    const double *prm = a.params + size_t(k0) * NNGP_NPARAM;
-    const T sigma2 = FACT ? T(1) : T(prm[0]);
-    const double phi = SWEEP ? 1.0 : prm[1];  // sweep: coordinates stay unscaled, u = phi_k * distance per vector
+    // parameter vector k, component c: from device memory, or straight from the kernel arguments (a host-pointer
+    // call with K <= NNGP_PV_MAX needs no H2D copy: the values sit in the constant bank when the block starts)
+    auto prm_at = [&](int k, int c) -> double { return a.params ? a.params[size_t(k) * NNGP_NPARAM + c] : a.pv[k][c]; };
+    const T sigma2 = FACT ? T(1) : T(prm_at(k0, 0));
+    const double phi = SWEEP ? 1.0 : prm_at(k0, 1);  // sweep: coordinates stay unscaled, u = phi_k * distance per vector
     // {diagonal without eps2, scale of eps2}: read from shared memory where they are used -- the main loop is at
     // its register limit and pays for every value kept live across it
     __shared__ double s_diag[2];
     if (threadIdx.x == 0) {
-        const double inv_s2 = FACT && !SWEEP ? 1.0 / prm[0] : 1.0;
-        s_diag[0] = FACT && !SWEEP ? fma(prm[2], inv_s2, 1.0) : prm[0] + prm[2];
+        const double p0 = prm_at(k0, 0), p2 = prm_at(k0, 2);
+        const double inv_s2 = FACT && !SWEEP ? 1.0 / p0 : 1.0;
+        s_diag[0] = FACT && !SWEEP ? fma(p2, inv_s2, 1.0) : p0 + p2;
         s_diag[1] = inv_s2;
     }
     const int m = a.m;
@@ -462,11 +465,12 @@ __global__ void __launch_bounds__(kThreads, MINB) fused_loglik_kernel(const Eval
     __shared__ double sw_prm[kSweepChunk][4];  // sweep: {phi, tau2 / sigma2, 1 / sigma2, log sigma2} per vector
     if constexpr (SWEEP) {
         if (threadIdx.x < kc) {
-            const double *pk = prm + threadIdx.x * NNGP_NPARAM;
-            sw_prm[threadIdx.x][0] = pk[1];
-            sw_prm[threadIdx.x][1] = pk[2] / pk[0];
-            sw_prm[threadIdx.x][2] = 1.0 / pk[0];
-            sw_prm[threadIdx.x][3] = log(pk[0]);
+            const int kv = k0 + int(threadIdx.x);
+            const double pk0 = prm_at(kv, 0);
+            sw_prm[threadIdx.x][0] = prm_at(kv, 1);
+            sw_prm[threadIdx.x][1] = prm_at(kv, 2) / pk0;
+            sw_prm[threadIdx.x][2] = 1.0 / pk0;
+            sw_prm[threadIdx.x][3] = log(pk0);
         }
         for (int kk = 0; kk < kSweepChunk; ++kk) {
             accbuf[kk * 128] = 1.0; accbuf[kk * 128 + 32] = 0.0; accbuf[kk * 128 + 64] = 0.0; accbuf[kk * 128 + 96] = 0.0;
@@ -997,7 +1001,7 @@ __global__ void __launch_bounds__(kThreads, MINB) fused_loglik_kernel(const Eval
                     // kernel it stays live across the main loop, which is at its register limit and spills for it
                     unsigned int by_;
                     asm volatile("mov.u32 %0, %%ctaid.y;" : "=r"(by_));
-                    const double s2 = a.params[size_t(by_) * NNGP_NPARAM];
+                    const double s2 = prm_at(int(by_), 0);
                     ls2 = log(s2);
                     is2 = 1.0 / s2;
                 }
@@ -1011,11 +1015,7 @@ __global__ void __launch_bounds__(kThreads, MINB) fused_loglik_kernel(const Eval
                 __syncthreads();
                 peer_allreduce3(a.px, k0 + kk, tot[0], tot[1], tot[2], &fin[kThreads / 2][0], tot);
             }
-            if (threadIdx.x == 0) {
-                a.out[size_t(k0 + kk) * 3 + 0] = tot[0];
-                a.out[size_t(k0 + kk) * 3 + 1] = tot[1];
-                a.out[size_t(k0 + kk) * 3 + 2] = tot[2];
-            }
+            if (threadIdx.x == 0) publish_result(a, k0 + kk, tot);
         }
         if (threadIdx.x == 0) a.counters[blockIdx.y] = 0u;  // ready for the next launch
         TL(7, threadIdx.x == 0);

@@ -18,16 +18,18 @@
 
 #include "../../include/nngp_b200.h"
 
-// Cross-GPU exchange of the K x 3 statistics over NVLink peer memory (one process per GPU, buffers
-// shared through CUDA IPC).  Every rank owns one exchange buffer:
-//   slots [2][NNGP_MAX_PEERS][K_cap * 3] doubles, then flags [2][NNGP_MAX_PEERS][K_cap] generations;
-// the leading index is the parity of the exchange generation, the second the WRITING rank.
+// Cross-GPU exchange of the K x 3 statistics over NVLink peer memory (buffers of other processes mapped
+// through CUDA IPC, buffers of other devices of this process through cudaDeviceEnablePeerAccess).  Every
+// rank owns one exchange buffer of 16-byte lines
+//   lines [2][NNGP_MAX_PEERS][K_cap][3] x {lo32(value), gen32, hi32(value), gen32};
+// the leading index is the parity of the exchange generation, the second the WRITING rank.  A line is
+// written by ONE 16-byte store and carries its own generation stamp beside each half of the value, so the
+// reader needs neither a separate flag nor a fence: it polls the line until both stamps match.
 constexpr int NNGP_MAX_PEERS = 8;
 struct PeerExchange {
     int world = 0, rank = 0, K_cap = 0;
-    unsigned long long gen = 0;                  // this launch's generation (>= 1), same on all ranks
-    double *slots[NNGP_MAX_PEERS] = {};          // rank r's buffer as mapped in this process
-    unsigned long long *flags[NNGP_MAX_PEERS] = {};
+    unsigned int gen = 0;                        // this launch's generation (>= 1), same on all ranks
+    uint4 *lines[NNGP_MAX_PEERS] = {};           // rank r's buffer as mapped in this process
 };
 
 struct nngp_handle {
@@ -49,8 +51,13 @@ struct nngp_handle {
     double4 *pts = nullptr;
     double *d_ystage = nullptr;  // n doubles: landing buffer of nngp_set_y (allocated on first use)
     double *eps2 = nullptr;
+    // neighbour table: rows [nbr_row0, nbr_row0 + nbr_rows) of the n x m table (all n rows unless the table
+    // was built for the shard only, nngp_build_neighbors_shard); kernels index it through nbr_base()
     int32_t *nbr = nullptr;
+    int64_t nbr_row0 = 0, nbr_rows = 0;
     bool has_nbr = false;
+    int32_t *nbr_base() const { return nbr - nbr_row0 * m; }
+    bool holds_rows(int64_t i0, int64_t i1) const { return i0 >= nbr_row0 && i1 <= nbr_row0 + nbr_rows; }
 
     // evaluation scratch (grown on demand)
     int K_cap = 0;
@@ -61,7 +68,16 @@ struct nngp_handle {
     unsigned int *d_counters = nullptr;  // K_cap tickets for the last-block reduction
     unsigned int *d_tile_counter = nullptr;
     double *d_exp2tab = nullptr;   // 2^(j/2048), j < 2048 (built once at nngp_create)
-    double *h_stage = nullptr;     // pinned: K_cap x (4 + 3)
+    double *h_stage = nullptr;     // pinned: K_cap x 4 parameter staging (K > NNGP_PV_MAX only)
+    // results of the host-pointer calls land in MAPPED pinned host memory, written by the kernel's last
+    // block itself, followed by a sequence stamp per blockIdx.y the host polls: no D2H copy, no stream sync
+    uint4 *h_out = nullptr;                  // K_cap x 3 stamped lines (host address == device address under UVA)
+    unsigned int seq = 0;                    // stamp of the last host-pointer evaluation
+    int32_t *d_viol = nullptr;               // violation counter of nngp_set_neighbors' table check
+
+    // stage-1 scratch of the grid search, kept between builds (grown on demand, freed with the handle)
+    void *knn_scratch[5] = {};
+    size_t knn_scratch_bytes[5] = {};
 
     // peer exchange (multi-GPU): own buffer, peers' buffers opened through CUDA IPC
     void *xbuf = nullptr;
@@ -72,21 +88,28 @@ struct nngp_handle {
 
     int64_t launches = 0;
     std::string err;
+
+    // multi-device handle (nngp_create_multi): one sub-handle per device, driven by worker threads
+    struct nngp_group *group = nullptr;
 };
 
 // Arguments of the fused covariance + factorisation + reduction kernel.
+constexpr int NNGP_PV_MAX = 8;  // parameter vectors that travel in the kernel arguments (no H2D copy)
 struct EvalArgs {
     const double4 *pts;
     const double *eps2;   // nullable
-    const int32_t *nbr;   // n x m
+    const int32_t *nbr;   // n x m (base of row 0; a handle may hold a window of rows only)
     int64_t lo, hi;       // rows to evaluate
     int m;
-    const double *params;     // K x 4 (device)
+    const double *params;     // K x 4 (device), or NULL: the vectors are in pv[] (K <= NNGP_PV_MAX)
+    double pv[NNGP_PV_MAX][NNGP_NPARAM];
     int K;                    // parameter vectors of this launch
     const double *exp2tab;    // 2^(j/2048), j < 2048
     double *partials;         // gridDim.y x gridDim.x x 3
     unsigned int *counters;   // gridDim.y
-    double *out;              // gridDim.y x 3
+    double *out;              // gridDim.y x 3 doubles in device memory, or NULL:
+    uint4 *hout;              //   gridDim.y x 3 self-stamped 16-byte lines in MAPPED pinned host memory (ll_store)
+    unsigned int seq;         //   the stamp of this evaluation
     // optional per-location outputs (rows lo..hi map to output rows 0..hi-lo); any may be null
     int emit;                 // 0: reduction only
     double *B, *F, *CN, *cc, *cs;
@@ -102,16 +125,24 @@ cudaError_t launch_knn_ordered(nngp_handle *h, int m, int tile_offset, int tile_
                                cudaStream_t stream);
 cudaError_t launch_knn_plain(nngp_handle *h, int k, int32_t *d_table, cudaStream_t stream);
 cudaError_t launch_fill_i32(nngp_handle *h, int32_t *p, int64_t count, int32_t v, cudaStream_t stream);
-// brute force restricted to the query tiles covering rows [first_row, n_rows) of the ordering;
-// candidates of row i are j < min(i, cand_cap)
+// brute force for rows [first_row, n_rows) of the ordering (whole query tiles are searched, only these rows are
+// written); candidates of row i are j < min(i, cand_cap).  d_table is the base of row 0.
 cudaError_t launch_knn_brute_rows(nngp_handle *h, int m, int64_t first_row, int64_t n_rows, int64_t cand_cap,
                                   int32_t *d_table, cudaStream_t stream);
 // grid search (knn_grid.cu) for rows [row_lo, row_hi), candidates j < min(i, cand_cap); *used = 0 when
 // the data does not suit a grid
+// `table` is the base of row 0; window = true: only rows [row_lo, row_hi) exist behind it (nothing else is written)
 cudaError_t launch_knn_grid(nngp_handle *h, bool ordered, int m, int64_t row_lo, int64_t row_hi, int64_t cand_cap,
-                            int32_t *table, cudaStream_t stream, int force, int *used);
+                            int32_t *table, bool window, cudaStream_t stream, int force, int *used);
+// counts into *d_viol the rows i in [i0, i1) of `rows` (row i0 first) that hold an entry outside [-1, i) or a
+// valid entry after a -1
+cudaError_t launch_validate_table(nngp_handle *h, const int32_t *rows, int m, int64_t i0, int64_t i1, int32_t *d_viol,
+                                  cudaStream_t stream);
+// device memory that stays with the handle between calls (slot 0..4), grown on demand
+cudaError_t scratch_get(nngp_handle *h, int slot, size_t bytes, void **p);
 // publishes zeros for a rank whose shard is empty (it still takes part in the exchange)
-cudaError_t launch_peer_zero(nngp_handle *h, const PeerExchange &px, int K, double *d_out, cudaStream_t stream);
+cudaError_t launch_peer_zero(nngp_handle *h, const PeerExchange &px, int K, double *d_out, uint4 *hout, unsigned int seq,
+                             cudaStream_t stream);
 // device-side packing of the records + bounding box (pack.cu); synchronises `stream`
 cudaError_t launch_pack_records(nngp_handle *h, const double *d_coords, const double *d_y, const double *d_eps2,
                                 cudaStream_t stream);

@@ -64,7 +64,53 @@ __global__ void __launch_bounds__(kBlock) scatter_lane_kernel(const double *__re
         reinterpret_cast<double *>(pts + i)[lane] = v[i];
 }
 
+// one thread per row of an injected neighbour table: entries in [-1, i), padding at the tail only
+__global__ void __launch_bounds__(kBlock) validate_table_kernel(const int32_t *__restrict__ rows, int m, int64_t i0, int64_t i1,
+                                                                 int32_t *viol)
+{
+    int bad = 0;
+    for (int64_t i = i0 + blockIdx.x * int64_t(kBlock) + threadIdx.x; i < i1; i += int64_t(gridDim.x) * kBlock) {
+        const int32_t *row = rows + (i - i0) * m;
+        bool pad = false, ok = true;
+        for (int k = 0; k < m; ++k) {
+            const int32_t e = row[k];
+            if (e == -1) pad = true;
+            else if (e < -1 || e >= i || pad) ok = false;
+        }
+        bad += !ok;
+    }
+    if (bad) atomicAdd(viol, bad);
+}
+
 }  // namespace nngp_pack
+
+cudaError_t launch_validate_table(nngp_handle *h, const int32_t *rows, int m, int64_t i0, int64_t i1, int32_t *d_viol,
+                                  cudaStream_t stream)
+{
+    using namespace nngp_pack;
+    cudaError_t e = cudaMemsetAsync(d_viol, 0, sizeof(int32_t), stream);
+    if (e != cudaSuccess) return e;
+    int grid = int(std::min<int64_t>((i1 - i0 + kBlock - 1) / kBlock, int64_t(h->num_sms) * 8));
+    if (grid < 1) grid = 1;
+    validate_table_kernel<<<grid, kBlock, 0, stream>>>(rows, m, i0, i1, d_viol);
+    ++h->launches;
+    return cudaGetLastError();
+}
+
+cudaError_t scratch_get(nngp_handle *h, int slot, size_t bytes, void **p)
+{
+    if (h->knn_scratch_bytes[slot] < bytes) {
+        if (h->knn_scratch[slot]) cudaFree(h->knn_scratch[slot]);
+        h->knn_scratch[slot] = nullptr;
+        h->knn_scratch_bytes[slot] = 0;
+        const size_t want = bytes + bytes / 8;  // a little headroom: the next build is often slightly larger
+        cudaError_t e = cudaMalloc(&h->knn_scratch[slot], want);
+        if (e != cudaSuccess) return e;
+        h->knn_scratch_bytes[slot] = want;
+    }
+    *p = h->knn_scratch[slot];
+    return cudaSuccess;
+}
 
 cudaError_t launch_scatter_lane(nngp_handle *h, const double *d_v, int lane, cudaStream_t stream)
 {

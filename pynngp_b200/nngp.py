@@ -12,6 +12,14 @@ What is kept from the reference (drop-in contract):
 What is added: ``loglik``, ``loglik_terms``, ``loglik_batch``, ``factors`` and keyword-only engine
 options.  There is no CPU fallback: constructing an ``NNGP`` without a B200 raises.
 
+GPUs.  ``devices=None`` (default) uses every visible B200 of this process when it is a plain process (the
+reference's caller writes ``NNGP(t, y, eps, refType, m, cov)`` and nothing else, nngp.py:6), and the local
+rank's GPU under ``torchrun``; ``devices=int`` pins one GPU, ``devices=[...]`` lists them.  Several GPUs
+in one process are one multi-device handle of the C library (``nngp_create_multi``): the ordering is split in
+contiguous blocks, each device searches and keeps the neighbour rows of its block, and an evaluation is one
+kernel per device -- launched in parallel by the library's own threads -- whose tails add the statistics
+up over NVLink peer memory.
+
 Reference sets other than T (nngp.py:32-40, 68-71).  ``refType = ('subset', nRef)`` and
 ``('random', nRef, bounds)`` crash upstream (``self.typ`` is never set, nngp.py:34); here they build what
 the reference's code intends: ``s``, ``ws`` (5-NN regression of (t, y) evaluated at s), ``Ns`` (ordered
@@ -87,7 +95,7 @@ class QueryNeighborSets:
 
 
 class NNGP(object):
-    def __init__(self, t, y, eps, refType, m, cov, *, dtype="float64", device=None, neighbors=None,
+    def __init__(self, t, y, eps, refType, m, cov, *, dtype="float64", devices=None, device=None, neighbors=None,
                  group=None, knn="auto", seed=None):
         self.t = t  # ordinates
         self.y = y  # abscissae
@@ -102,9 +110,15 @@ class NNGP(object):
         self._knn = knn  # stage-1 algorithm: cell-grid search (bit-identical) unless the data defeats it
         self._group = group
         self._rank, self._world = _dist.get_world(group)
-        if device is None:
-            device = self._local_device()
-        self._engine = _lib.Engine(device=device, dtype=dtype)
+        if devices is None:
+            devices = device  # `device=` is the older spelling of `devices=int`
+        if devices is None:
+            devices = self._default_devices()
+        elif self._world > 1 and not isinstance(devices, int):
+            raise ValueError("under torch.distributed every rank drives ONE GPU: pass devices=<int> (or nothing)")
+        if isinstance(devices, (list, tuple)) and len(devices) == 1:
+            devices = int(devices[0])
+        self._engine = _lib.Engine(device=devices, dtype=dtype)
         self._ycol = None
         self._timings = {}
         self._seed = seed  # S != T only: None = numpy's global RNG as in the reference (nngp.py:36, 40)
@@ -116,14 +130,31 @@ class NNGP(object):
         self._make_t_neighbor_sets()
         self._ws = None
         self._peer_ok = self._setup_peer_exchange()
+        k = self._kernel
+        self._fast_terms = (self._y2d.shape[1] == 1 and self._ref_kind != "random" and (self._world == 1 or self._peer_ok)
+                            and None not in (k.sigma2, k.phi, k.tau2))
 
     # ---- construction steps, named as in the reference -----------------------------------------
-    def _local_device(self):
+    def _default_devices(self):
+        """torchrun: the local rank's GPU.  A plain process: every visible GPU (one multi-device handle), so an
+        unchanged caller of the reference's constructor gets the whole box; NNGP_DEVICES=0 or =0,1,.. overrides."""
         import os
 
-        return int(os.environ.get("LOCAL_RANK", "0")) if self._world > 1 else 0
+        if self._world > 1:
+            return int(os.environ.get("LOCAL_RANK", "0"))
+        env = os.environ.get("NNGP_DEVICES")
+        if env:
+            devs = [int(d) for d in env.split(",") if d.strip() != ""]
+            return devs[0] if len(devs) == 1 else devs
+        n = _lib.device_count()
+        return 0 if n <= 1 else list(range(min(n, 8)))
 
-    def _setup_peer_exchange(self, K_cap=256):
+    @property
+    def devices(self):
+        """The CUDA devices this object computes on."""
+        return list(self._engine.devices)
+
+    def _setup_peer_exchange(self, K_cap=128):
         """Multi-GPU on one node: map every rank's exchange buffer (CUDA IPC) so the fused kernel sums the
         statistics over NVLink peer memory itself (nngp_loglik_device_allreduce).  Any failure on any rank
         -- ranks on different nodes, no P2P, NNGP_PEER_EXCHANGE=0 -- leaves all ranks on the NCCL allreduce."""
@@ -247,15 +278,14 @@ class NNGP(object):
         if self._ycol == c:
             return
         eps2 = None if self._eps2 is None else np.ascontiguousarray(self._eps2[:, c])
-        if self._ycol is None or self._eps2 is not None:
-            had_table = self._engine.m > 0
-            table = self._table if had_table else None
+        if self._ycol is None:
             self._engine.set_data(self._coords, np.ascontiguousarray(self._y2d[:, c]), eps2)
-            if had_table:
-                self._engine.set_neighbors(table)
-                self._engine.set_shard(*self._shard)
         else:
+            # a column switch replaces the response (and its eps) in place: coordinates, neighbour table and
+            # shard stay resident (nngp_set_y / nngp_set_eps2)
             self._engine.set_y(np.ascontiguousarray(self._y2d[:, c]))
+            if eps2 is not None:
+                self._engine.set_eps2(eps2)
         self._ycol = c
 
     def _make_s_neighbor_sets(self, neighbors=None):
@@ -267,35 +297,35 @@ class NNGP(object):
         if isinstance(neighbors, (str, bytes)) or hasattr(neighbors, "__fspath__"):
             neighbors = np.load(neighbors)  # a table written by save_neighbors()
         if neighbors is not None:
-            eng.set_neighbors(neighbors)
+            neighbors = np.asarray(neighbors)
+            if neighbors.ndim != 2 or neighbors.shape != (eng.n, self.m) or neighbors.dtype.kind not in "iu":
+                raise ValueError(f"neighbors must be an integer table of shape ({eng.n}, {self.m}): got "
+                                 f"{neighbors.dtype} {neighbors.shape}")
+            eng.set_neighbors(neighbors)  # checked on the device: entries of row i in [-1, i), padding last
+            eng.set_shard(*self._shard)
         elif self._ref_kind != "S=T":
             # nngp.py:49-62 on s (rows [0, nRef): ordered search among predecessors) and nngp.py:68-71
             # for the rows of T - S (their m nearest reference sites, any index); every rank builds the
-            # whole table
-            eng.build_neighbors_grid(self.m, 0, self._n_ref, self._knn)
-            table = eng.get_neighbor_rows(0, self._n_ref)
+            # whole table (on one device: a multi-device handle only searches whole shards)
+            one = eng if len(eng.devices) == 1 else _lib.Engine(device=eng.device, dtype=eng.dtype)
+            try:
+                if one is not eng:
+                    one.set_data(self._coords, np.zeros(eng.n), None)
+                one.build_neighbors_grid(self.m, 0, self._n_ref, self._knn)
+                table = one.get_neighbor_rows(0, self._n_ref)
+            finally:
+                if one is not eng:
+                    one.close()
             if eng.n > self._n_ref:
                 table = np.concatenate([table, self._nt_table[self._rows[self._n_ref:]]])
             eng.set_neighbors(table)
             eng.set_shard(*self._shard)
             neighbors = table
-        elif self._world == 1:
-            eng.build_neighbors_grid(self.m, 0, eng.n, self._knn)
         else:
-            import torch
-
-            if self._knn == "brute":
-                # quadratic work grows with i: tiles dealt round-robin from the heavy end
-                off, stride = _dist.knn_tile_split(self._rank, self._world)
-                eng.build_neighbors(self.m, off, stride)
-            else:
-                # grid search is ~uniform per row: every rank builds the rows of its own shard
-                eng.build_neighbors_grid(self.m, self._shard[0], self._shard[1], self._knn)
-            self._timings["knn_local_s"] = time.perf_counter() - t0
-            view = _dist.DevicePtrView(eng.neighbors_device_ptr(), (eng.n, eng.m), "<i4")
-            tab = torch.as_tensor(view, device=f"cuda:{eng.device}")
-            _dist.assemble_table_max(tab, self._group)  # unset rows hold -2
-            torch.cuda.synchronize(eng.device)
+            # every GPU (a rank under torchrun, a device of a multi-device handle) searches and keeps the rows of
+            # its own shard only: the likelihood needs nothing else, so stage 1 involves no exchange at all.  The
+            # grid search costs about the same per row wherever the row sits in the ordering.
+            eng.build_neighbors_shard(self.m, self._knn)
         self._timings["knn_s"] = time.perf_counter() - t0
         self._table_host = None if neighbors is None else np.ascontiguousarray(neighbors, dtype=np.int32)
         self._Ns = None
@@ -305,8 +335,42 @@ class NNGP(object):
         """(n, m) int32 neighbour table on the host; downloaded from the device the first time it is
         read (the likelihood itself never needs it on the host)."""
         if self._table_host is None:
+            row0, rows = self._engine.neighbor_window()
+            if row0 != 0 or rows != self._engine.n:
+                # a rank of a multi-process run holds the rows of its shard only.  Reading the whole table
+                # (`Ns`, save_neighbors, the accessors) must not be a collective -- one rank alone may ask -- so
+                # the rank searches the missing rows itself: coordinates are replicated, and the whole search
+                # costs milliseconds (gather_table() is the collective alternative)
+                self._engine.build_neighbors_grid(self.m, 0, self._engine.n, self._knn)
             self._table_host = self._engine.get_neighbors()
         return self._table_host
+
+    def gather_table(self):
+        """Collective (every rank must call it): assembles the (n, m) table from the row blocks the ranks hold
+        -- one all_gather of ceil(n / world) rows per rank instead of a search of the missing rows."""
+        if self._table_host is not None or self._world == 1:
+            return self._table
+        import torch
+        import torch.distributed as dist
+
+        eng = self._engine
+        row0, rows = eng.neighbor_window()
+        per = -(-eng.n // self._world)
+        if (row0, rows) != tuple((self._shard[0], self._shard[1] - self._shard[0])):
+            return self._table
+        cuda = dist.get_backend(self._group) == "nccl"
+        mine = torch.full((per, eng.m), _lib.ROW_UNSET, dtype=torch.int32)
+        mine[:rows] = torch.from_numpy(eng.get_neighbor_rows(row0, row0 + rows))
+        if cuda:
+            mine = mine.to(f"cuda:{eng.device}")
+        parts = [torch.empty_like(mine) for _ in range(self._world)]
+        dist.all_gather(parts, mine, group=self._group)
+        table = np.empty((eng.n, eng.m), dtype=np.int32)
+        for r, part in enumerate(parts):
+            lo, hi = _dist.shard_bounds(eng.n, r, self._world)
+            table[lo:hi] = part[: hi - lo].cpu().numpy()
+        self._table_host = table
+        return table
 
     @property
     def Ns(self):
@@ -432,17 +496,27 @@ class NNGP(object):
         buffer, the kernel writes this rank's partials, an NCCL allreduce follows on the same stream with no
         host round trip in between, and one pinned D2H copy returns the totals."""
         K = params.shape[0]
-        if self._peer_ok and K <= self._peer_K_cap:
+        if self._peer_ok:
             # the kernel's last block sums over the ranks through NVLink peer memory: no torch, no NCCL
             total = np.zeros((K, _lib.NSTAT))
+            cap = self._peer_K_cap
             for c in range(self._y2d.shape[1]):
                 self._set_column(c)
-                total += self._engine.loglik_allreduce(self._kernel.kernel_id, params)
+                for k0 in range(0, K, cap):
+                    total[k0:k0 + cap] += self._engine.loglik_allreduce(self._kernel.kernel_id, params[k0:k0 + cap])
             if np.isnan(total).any():
                 raise RuntimeError("the cross-GPU exchange timed out: a rank never launched its evaluation")
             return total
         import torch
+        import torch.distributed as tdist
 
+        if tdist.get_backend(self._group) != "nccl":
+            # a host-side group (gloo): this rank's partial statistics, summed by the group's allreduce
+            total = np.zeros((K, _lib.NSTAT))
+            for c in range(self._y2d.shape[1]):
+                self._set_column(c)
+                total += self._engine.loglik(self._kernel.kernel_id, params)
+            return np.asarray(_dist.allreduce_stats(total, self._group))
         dev = torch.device("cuda", self._engine.device)
         buf = getattr(self, "_shard_bufs", None)
         if buf is None or buf["K"] < K:
@@ -479,7 +553,17 @@ class NNGP(object):
 
     def loglik_terms(self, sigma2=None, phi=None, tau2=None):
         """(sum_i log F_i, sum_i r_i^2 / F_i) -- the reduction BASELINE.json's north_star names."""
-        st = self.loglik_batch(self._params(sigma2, phi, tau2)[None, :])[0]
+        if self._fast_terms:
+            # one response column on one handle (or a connected peer exchange): the parameters travel by value
+            # through nngp_loglik_terms and the statistics come back through mapped memory -- no arrays here
+            k = self._kernel
+            st = self._engine.loglik_terms(
+                k.kernel_id, float(k.sigma2 if sigma2 is None else sigma2), float(k.phi if phi is None else phi),
+                float(k.tau2 if tau2 is None else tau2))
+            if st[0] != st[0]:
+                raise RuntimeError("the cross-GPU exchange timed out: a rank never launched its evaluation")
+        else:
+            st = self.loglik_batch(self._params(sigma2, phi, tau2)[None, :])[0]
         if st[2] > 0:
             raise FloatingPointError(f"{int(st[2])} location(s) had a non-positive-definite neighbour covariance")
         return float(st[0]), float(st[1])
@@ -560,23 +644,24 @@ class NNGP(object):
         if q == 0:
             return mean.reshape((0,) + np.shape(self.y)[1:]), var.reshape((0,) + np.shape(self.y)[1:])
         eng = _lib.Engine(device=self._engine.device, dtype=self._engine.dtype)
-        coords = np.concatenate([self._coords[:n], tn])
-        B = F = tab = None
-        for c in range(ncol):
-            if B is None or self._eps2 is not None:  # weights depend on the column only through eps
-                eps2 = None if self._eps2 is None else np.concatenate([self._eps2[:n, c], np.zeros(q)])
-                eng.set_data(coords, np.concatenate([self._y2d[:n, c], np.zeros(q)]), eps2)
-                if tab is None:
-                    eng.build_neighbors_capped(m, n, n + q, n, self._knn)
-                    tab = eng.get_neighbor_rows(n, n + q)
-                    full = eng.get_neighbors() if self._eps2 is not None else None
-                else:
-                    eng.set_neighbors(full)
-                B, F = eng.factors(self._kernel.kernel_id, prm, n, n + q)
-            yn = np.where(tab >= 0, self._y2d[np.maximum(tab, 0), c], 0.0)
-            mean[:, c] = (B * yn).sum(axis=1)
-            var[:, c] = F
-        eng.close()
+        try:
+            coords = np.concatenate([self._coords[:n], tn])
+            B = F = tab = None
+            for c in range(ncol):
+                if B is None or self._eps2 is not None:  # weights depend on the column only through eps
+                    if tab is None:
+                        eps2 = None if self._eps2 is None else np.concatenate([self._eps2[:n, c], np.zeros(q)])
+                        eng.set_data(coords, np.concatenate([self._y2d[:n, c], np.zeros(q)]), eps2)
+                        eng.build_neighbors_capped(m, n, n + q, n, self._knn)
+                        tab = eng.get_neighbor_rows(n, n + q)
+                    else:  # the next column's eps: replaced in place, coordinates and table stay
+                        eng.set_eps2(np.concatenate([self._eps2[:n, c], np.zeros(q)]))
+                    B, F = eng.factors(self._kernel.kernel_id, prm, n, n + q)
+                yn = np.where(tab >= 0, self._y2d[np.maximum(tab, 0), c], 0.0)
+                mean[:, c] = (B * yn).sum(axis=1)
+                var[:, c] = F
+        finally:
+            eng.close()
         shape = (q,) + np.shape(self.y)[1:]
         return mean.reshape(shape), var.reshape(shape)
 

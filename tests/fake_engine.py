@@ -35,9 +35,12 @@ class FakeEngine:
     def __init__(self, device=0, dtype="float64"):
         if dtype not in ("float64", "float32"):
             raise ValueError("dtype must be 'float64' or 'float32'")
-        self.device, self.dtype = int(device), str(dtype)
+        # a list of devices is a multi-device handle (nngp_create_multi): the same contract, totals returned
+        self.devices = [int(d) for d in device] if isinstance(device, (list, tuple)) else [int(device)]
+        self.device, self.dtype = self.devices[0], str(dtype)
         self.n = self.D = self.m = 0
         self._tab = None
+        self._win = (0, 0)  # rows of the table this handle holds
         self._closed = False
 
     def close(self):
@@ -80,19 +83,40 @@ class FakeEngine:
         assert algo in ("auto", "grid", "brute") and 1 <= m <= 32 and cand_cap >= 1
         tab = np.full((self.n, m), ROW_UNSET, dtype=np.int32)  # rows outside the range are unset
         tab[row_lo:row_hi] = knn_capped(self._s, m, row_lo, row_hi, cand_cap)
-        self._tab, self.m = tab, int(m)
+        self._tab, self.m, self._win = tab, int(m), (0, self.n)
         FakeEngine.launches += 1
+
+    def build_neighbors_shard(self, m, algo="auto"):
+        """nngp_build_neighbors_shard: the rows of the shard only; nothing else is held."""
+        lo, hi = self._shard
+        self.build_neighbors_capped(m, lo, hi, self.n, algo)
+        self._win = (lo, hi - lo)
+
+    def neighbor_window(self):
+        return self._win if self._tab is not None else (self._win[0], 0)
+
+    def _held(self, i0, i1):
+        r0, rows = self._win
+        if i1 > i0 and not (r0 <= i0 and i1 <= r0 + rows):
+            raise RuntimeError("the table of this handle holds the rows of its shard only")
 
     def set_neighbors(self, table):
         table = np.ascontiguousarray(table, dtype=np.int32)
         if table.ndim != 2 or table.shape[0] != self.n:
             raise ValueError("neighbour table must be (n, m) int32")
-        self._tab, self.m = table.copy(), table.shape[1]
+        # the device-side check of nngp_set_neighbors: entries of row i in [-1, i), padding at the tail
+        rows = np.arange(self.n)[:, None]
+        pad_then_valid = ((table[:, :-1] == -1) & (table[:, 1:] != -1)).any() if table.shape[1] > 1 else False
+        if (table < -1).any() or (table >= rows).any() or pad_then_valid:
+            raise RuntimeError("nngp_set_neighbors failed (1): invalid neighbour table")
+        self._tab, self.m, self._win = table.copy(), table.shape[1], (0, self.n)
 
     def get_neighbors(self):
+        self._held(0, self.n)
         return self._tab.copy()
 
     def get_neighbor_rows(self, i0, i1):
+        self._held(i0, i1)
         return self._tab[i0:i1].copy()
 
     def knn_plain(self, k):
@@ -110,9 +134,14 @@ class FakeEngine:
         params = np.atleast_2d(np.asarray(params, dtype=np.float64))
         assert params.shape[1] == 4
         lo, hi = self._shard
+        self._held(lo, hi)
         FakeEngine.launches += 1
         return np.array([orc.c_loglik(self._s, self._y, self._clean(), kernel_id, p[0], p[1], p[2], eps2=self._eps2,
                                       lo=lo, hi=hi) for p in params])
+
+    def loglik_terms(self, kernel_id, sigma2, phi, tau2):
+        st = self.loglik(kernel_id, [sigma2, phi, tau2, 0.0])[0]
+        return float(st[0]), float(st[1]), float(st[2])
 
     def factors(self, kernel_id, params, i0=0, i1=None, want_B=True, want_F=True):
         i1 = self.n if i1 is None else i1

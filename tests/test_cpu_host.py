@@ -138,6 +138,64 @@ def test_two_rank_gloo_combination(tmp_path):
     assert r.stdout.count("ok") == 2
 
 
+_CLASS_WORKER = r'''
+import os, sys
+import numpy as np
+import torch.distributed as dist
+sys.path.insert(0, os.environ["NNGP_ROOT"]); sys.path.insert(0, os.path.join(os.environ["NNGP_ROOT"], "tests"))
+from fake_engine import FakeEngine
+from oracle import nngp_oracle as orc
+from pynngp_b200 import _lib, Matern
+from pynngp_b200.synthetic import synthetic
+_lib.Engine = FakeEngine  # the oracle-backed stand-in: this test is about the class's sharded host logic
+import pyNNGP
+
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+s, y = synthetic(1501, 2, 3)
+y2 = np.stack([y, 0.5 * y], axis=1)
+eps = np.stack([np.full(1501, 0.1), np.linspace(0.0, 0.2, 1501)], axis=1)
+obj = pyNNGP.NNGP(s, y2, eps, "S=T", 7, Matern(1.5, 1.0, 6.0, 0.1))
+full = orc.c_knn_ordered(s, 7)
+lo, hi = obj._shard
+assert (lo, hi) == ((1501 * rank) // world, (1501 * (rank + 1)) // world)
+# stage 1: the rank built and holds the rows of its own shard only -- no exchange happened
+assert obj._engine.neighbor_window() == (lo, hi - lo)
+assert np.array_equal(obj._engine.get_neighbor_rows(lo, hi), full[lo:hi])
+# stages 2-3: partial statistics of the shard, summed over the ranks, both response columns
+want = np.zeros(3)
+for c in range(2):
+    want += orc.c_loglik(s, y2[:, c], full, 1, 1.0, 6.0, 0.1, eps2=eps[:, c] ** 2)
+got = obj.loglik_batch([[1.0, 6.0, 0.1]])[0]
+np.testing.assert_allclose(got, want, rtol=1e-12)
+np.testing.assert_allclose(obj.loglik_terms(), want[:2], rtol=1e-12)
+# the whole table: collectively (all_gather of the row blocks) ...
+assert np.array_equal(obj.gather_table(), full)
+# ... or by ONE rank alone (no collective: it searches the missing rows itself)
+obj2 = pyNNGP.NNGP(s, y, 0.0, "S=T", 7, Matern(1.5, 1.0, 6.0, 0.1))
+if rank == 1:
+    assert np.array_equal(obj2._table, full) and obj2.Ns[5].tolist() == full[5, :5].tolist()
+np.testing.assert_allclose(obj2.loglik_terms(), orc.c_loglik(s, y, full, 1, 1.0, 6.0, 0.1)[:2], rtol=1e-12)
+dist.barrier()
+dist.destroy_process_group()
+print("rank", rank, "ok")
+'''
+
+
+def test_two_rank_gloo_class_shards_stage1_and_likelihood(tmp_path):
+    """world_size 2 over gloo: the drop-in class shards the ordering, every rank searches and keeps its own rows
+    (no table exchange), the statistics are summed over the ranks; `Ns` can be read by one rank alone."""
+    script = tmp_path / "class_worker.py"
+    script.write_text(_CLASS_WORKER)
+    env = dict(os.environ, NNGP_ROOT=ROOT, MASTER_ADDR="127.0.0.1")
+    r = subprocess.run(
+        [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+         "--master-addr", "127.0.0.1", "--master-port", "29619", str(script)],
+        env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert r.stdout.count("ok") == 2
+
+
 def test_bench_work_model_matches_the_survey():
     """bench.py's algorithmic figures are SURVEY 8(d4)'s: FP64-pipe instructions and compulsory HBM bytes per
     location at the four configurations."""

@@ -521,8 +521,11 @@ def test_cfg3_full_size_properties():
     c = CONFIGS["cfg3"]
     s, y = synthetic(c["n"], c["D"], c["seed"])
     e = engine(s, y)
-    e.build_neighbors(c["m"])
+    e.build_neighbors(c["m"])                                         # the quadratic brute-force kernel
     tab = e.get_neighbors()
+    e.build_neighbors_grid(c["m"])                                    # the production default (class, bench.py)
+    assert e.knn_used_grid()
+    assert np.array_equal(e.get_neighbors(), tab)                     # grid == brute force at production size
     n, m = tab.shape
     rows = np.arange(n)[:, None]
     assert (tab[m:] >= 0).all() and (tab < rows).all()                # predecessors only
@@ -544,6 +547,275 @@ def test_cfg3_full_size_properties():
     e.set_shard(lo, hi)
     st0 = orc.c_loglik(s, y, tab, 1, *P0[:3], lo=lo, hi=hi, threads=os.cpu_count() or 1)
     np.testing.assert_allclose(e.loglik(1, P0)[0][:2], st0[:2], rtol=RTOL64)
+
+
+def test_cfg2_whole_search_and_likelihood_vs_oracle():
+    """BASELINE.json configs[1]: n = 1e5, m = 15, 2-D exponential, search + likelihood on one GPU, the whole of
+    both against the threaded C oracle (no sampling)."""
+    import pyNNGP
+    from pynngp_b200 import Exponential
+
+    c = CONFIGS["cfg2"]
+    s, y = synthetic(c["n"], c["D"], c["seed"])
+    obj = pyNNGP.NNGP(s, y, 0.0, "S=T", c["m"], Exponential(**PARAMS))
+    assert obj._engine.knn_used_grid()
+    th = os.cpu_count() or 1
+    want_tab = orc.c_knn_ordered(s, c["m"], threads=th)
+    assert np.array_equal(obj._table, want_tab)
+    st0 = orc.c_loglik(s, y, want_tab, 0, *P0[:3], threads=th)
+    np.testing.assert_allclose(obj.loglik_terms(), st0[:2], rtol=RTOL64)
+    o32 = pyNNGP.NNGP(s, y, 0.0, "S=T", c["m"], Exponential(**PARAMS), dtype="float32", neighbors=want_tab)
+    np.testing.assert_allclose(o32.loglik_terms(), st0[:2], rtol=RTOL32)
+
+
+def test_cfg3_fp32_slab_and_whole():
+    """fp32 mode at cfg3's size (north_star: within 1e-4 relative of the fp64 oracle): a 40 000-row slab against the
+    oracle, and the whole evaluation against the engine's own fp64 result."""
+    c = CONFIGS["cfg3"]
+    s, y = synthetic(c["n"], c["D"], c["seed"])
+    e64 = engine(s, y)
+    e64.build_neighbors_grid(c["m"])
+    tab = e64.get_neighbors()
+    e32 = engine(s, y, None, "float32")
+    e32.set_neighbors(tab)
+    whole64, whole32 = e64.loglik(1, P0)[0], e32.loglik(1, P0)[0]
+    assert whole32[2] == 0
+    np.testing.assert_allclose(whole32[:2], whole64[:2], rtol=RTOL32)
+    lo, hi = 700000, 740000
+    e32.set_shard(lo, hi)
+    st0 = orc.c_loglik(s, y, tab, 1, *P0[:3], lo=lo, hi=hi, threads=os.cpu_count() or 1)
+    np.testing.assert_allclose(e32.loglik(1, P0)[0][:2], st0[:2], rtol=RTOL32)
+
+
+def test_cfg4_full_size():
+    """BASELINE.json configs[3]: n = 1e7, m = 30, 3-D Matern 3/2 through the drop-in class at full size.  No oracle
+    finishes the whole of it, so: structural invariants of the table, spot rows against the oracle's exact scan,
+    shards summing to the whole, and a 20 000-row slab of the likelihood against the oracle at 1e-10."""
+    import pyNNGP
+    from pynngp_b200 import Matern
+
+    c = CONFIGS["cfg4"]
+    s, y = synthetic(c["n"], c["D"], c["seed"])
+    n, m = c["n"], c["m"]
+    obj = pyNNGP.NNGP(s, y, 0.0, "S=T", m, Matern(1.5, **PARAMS))
+    eng = obj._engine
+    assert eng.knn_used_grid()
+    tab = obj._table
+    assert tab.shape == (n, m)
+    for a in range(0, n, 1 << 20):  # predecessors only, no padding past the ragged head (chunked: 3e8 entries)
+        blk = tab[a:a + (1 << 20)]
+        rows = np.arange(a, a + len(blk))[:, None]
+        assert (blk < rows).all() and (blk[max(m - a, 0):] >= 0).all()
+    assert all((tab[i, :i] >= 0).all() and (tab[i, i:] == -1).all() for i in range(m))
+    rng = np.random.default_rng(0)
+    pick = np.sort(rng.choice(np.arange(m, n), size=200000, replace=False))
+    d2 = ((s[tab[pick]] - s[pick, None, :]) ** 2).sum(-1)
+    assert (np.diff(d2, axis=1) >= 0).all()                           # ascending distance
+    assert all(len(set(r.tolist())) == m for r in tab[pick[:2000]])   # no repeated neighbour
+    for i in (30, 31, 4097, 5000001, n - 1):                          # spot rows: the oracle's exact scan
+        assert np.array_equal(tab[i], orc.c_knn_ordered(s, m, lo=i, hi=i + 1)[i]), i
+    whole = np.array(obj.loglik_batch([P0[:3]])[0])
+    assert whole[2] == 0
+    one = _lib.Engine(0)                                              # one device, explicit shards
+    one.set_data(s, y)
+    one.set_neighbors(tab)
+    acc = np.zeros(3)
+    for r in range(8):
+        one.set_shard((n * r) // 8, (n * (r + 1)) // 8)
+        acc += one.loglik(1, P0)[0]
+    np.testing.assert_allclose(acc[:2], whole[:2], rtol=1e-12)        # shards sum to the whole
+    lo, hi = 6000000, 6020000                                         # a slab against the oracle
+    one.set_shard(lo, hi)
+    st0 = orc.c_loglik(s, y, tab, 1, *P0[:3], lo=lo, hi=hi, threads=os.cpu_count() or 1)
+    got = one.loglik(1, P0)[0]
+    assert got[2] == 0 and st0[2] == 0
+    np.testing.assert_allclose(got[:2], st0[:2], rtol=RTOL64)
+    B, F = one.factors(1, P0, lo, lo + 64)                            # per-location factors of the same rows
+    B0, F0 = orc.c_factors(s, y, tab, 1, *P0[:3], lo=lo, hi=lo + 64)
+    np.testing.assert_allclose(F, F0, rtol=RTOL64)
+    assert (np.abs(B - B0) / np.maximum(np.abs(B0).max(axis=1, keepdims=True), 1.0)).max() <= RTOL64
+
+
+def test_known_answers_extended_precision(golden_dir):
+    """tests/golden/kat_cfg1.npz: cfg1 on the unmodified reference's own neighbour sets, evaluated in 80-bit
+    extended precision by textbook formulas (make_kat.py) -- independent of the oracle.  The engine's accessors
+    and statistics must reproduce it."""
+    k = np.load(os.path.join(golden_dir, "kat_cfg1.npz"))
+    g = np.load(os.path.join(golden_dir, "ns_cfg1.npz"))
+    c = CONFIGS["cfg1"]
+    s, y = synthetic(c["n"], c["D"], c["seed"])
+    e = engine(s, y, k["eps2"])
+    e.build_neighbors_grid(int(k["m"]))
+    tab = e.get_neighbors()
+    assert np.array_equal(tab, g["Ns"])                               # the reference's own sets
+    prm = np.array(list(k["params"]) + [0.0])
+    for kid in (0, 1):
+        st = e.loglik(kid, prm)[0]
+        assert st[2] == 0
+        np.testing.assert_allclose(st[:2], [k[f"k{kid}_sum_log_F"], k[f"k{kid}_sum_r2_over_F"]], rtol=RTOL64)
+        np.testing.assert_allclose(e.loglik_terms(kid, *prm[:3])[:2], st[:2], rtol=0)
+        for i in k["rows"]:
+            i = int(i)
+            CN, cc, cs = e.cov_blocks(kid, prm, i, i + 1)
+            B, F = e.factors(kid, prm, i, i + 1)
+            np.testing.assert_allclose(CN[0], k[f"k{kid}_CN_{i}"], rtol=1e-12, atol=1e-300)
+            np.testing.assert_allclose(cc[0], k[f"k{kid}_c_{i}"], rtol=1e-12, atol=1e-300)
+            np.testing.assert_allclose(cs[0], k[f"k{kid}_Cii_{i}"], rtol=1e-15)
+            np.testing.assert_allclose(B[0], k[f"k{kid}_b_{i}"], rtol=0, atol=RTOL64)
+            np.testing.assert_allclose(F[0], k[f"k{kid}_F_{i}"], rtol=RTOL64)
+
+
+def test_injected_table_is_validated():
+    """nngp_set_neighbors checks the table on the device: an entry outside [-1, i) or padding before a valid entry
+    is refused (NNGP_EINVAL) instead of being gathered from."""
+    s, y = synthetic(500, 2, 2)
+    e = engine(s, y)
+    good = orc.c_knn_ordered(s, 6)
+    e.set_neighbors(good)
+    for mutate in (lambda t: t.__setitem__((400, 2), 500),      # past the records
+                   lambda t: t.__setitem__((400, 2), 10**9),
+                   lambda t: t.__setitem__((7, 0), 7),          # itself
+                   lambda t: t.__setitem__((7, 0), 300),        # a successor: not causal
+                   lambda t: t.__setitem__((9, 1), -1),         # padding before a valid entry
+                   lambda t: t.__setitem__((9, 1), -5)):
+        bad = good.copy()
+        mutate(bad)
+        with pytest.raises(_lib.NNGPError):
+            e.set_neighbors(bad)
+    e.set_neighbors(good)
+    st0 = orc.c_loglik(s, y, good, 0, *P0[:3])
+    np.testing.assert_allclose(e.loglik(0, P0)[0][:2], st0[:2], rtol=RTOL64)
+    import pyNNGP
+
+    with pytest.raises(ValueError):
+        pyNNGP.NNGP(s, y, 0.0, "S=T", 5, None, neighbors=good)   # m of the table != m of the object
+
+
+def test_shard_window_table():
+    """nngp_build_neighbors_shard: the handle searches and holds the rows of its shard only (what a rank of a
+    multi-GPU run does); evaluations and per-location outputs work inside the window, nothing outside exists."""
+    s, y = synthetic(30000, 2, 5)
+    full = engine(s, y)
+    full.build_neighbors_grid(15)
+    tab = full.get_neighbors()
+    for lo, hi, algo in ((0, 3000, "auto"), (3000, 9000, "auto"), (9000, 30000, "auto"), (100, 5000, "brute"), (12345, 12345, "auto")):
+        e = engine(s, y)
+        e.set_knn_tuning(1.0, 1024)
+        e.set_shard(lo, hi)
+        e.build_neighbors_shard(15, algo)
+        assert e.neighbor_window() == (lo, hi - lo)
+        assert np.array_equal(e.get_neighbor_rows(lo, hi), tab[lo:hi])
+        full.set_shard(lo, hi)
+        assert np.array_equal(e.loglik(1, P0), full.loglik(1, P0))   # same rows, same launch shape: bitwise
+        if hi > lo:
+            with pytest.raises(_lib.NNGPError):
+                e.get_neighbors()                                      # the whole table is not here
+            B, F = e.factors(1, P0, lo, min(lo + 50, hi))
+            B0, F0 = full.factors(1, P0, lo, min(lo + 50, hi))
+            assert np.array_equal(B, B0) and np.array_equal(F, F0)
+            e.set_shard(0, 30000)
+            if (lo, hi) != (0, 30000):
+                with pytest.raises(_lib.NNGPError):
+                    e.loglik(1, P0)                                    # a shard the table does not cover
+
+
+def test_host_result_path_stress():
+    """1000 back-to-back host-pointer evaluations with alternating K: the parameters travel in the kernel arguments
+    (K <= 8) or through the staging copy (K > 8), the statistics come back through stamped lines in mapped host
+    memory.  Every repetition must return bitwise the same numbers."""
+    s, y = synthetic(4000, 2, 6)
+    e = engine(s, y)
+    e.build_neighbors_grid(15)
+    rng = np.random.default_rng(1)
+    K = 11
+    prm = np.stack([rng.uniform(0.5, 2, K), rng.uniform(3, 30, K), rng.uniform(0.01, 0.5, K), np.zeros(K)], 1)
+    want = {k: e.loglik(1, prm[:k]) for k in (1, 2, 5, 8, 9, 11)}
+    one = e.loglik_terms(1, *prm[0, :3])
+    assert one == tuple(want[1][0])
+    st0 = orc.c_loglik(s, y, e.get_neighbors(), 1, *prm[0, :3])
+    np.testing.assert_allclose(one[:2], st0[:2], rtol=RTOL64)
+    for it in range(1000):
+        k = (1, 5, 2, 11, 8, 9)[it % 6]
+        assert np.array_equal(e.loglik(1, prm[:k]), want[k]), (it, k)
+        if it % 7 == 0:
+            assert e.loglik_terms(1, *prm[0, :3]) == one
+
+
+def _need_gpus(k):
+    if _lib.device_count() < k:
+        pytest.skip(f"needs {k} GPUs")
+
+
+def test_multi_device_handle_matches_single():
+    """nngp_create_multi: ONE process, one handle over several GPUs -- skipped on a 1-GPU box.  Table,
+    statistics, per-location outputs and the host-path stress must agree with the single-device engine."""
+    _need_gpus(2)
+    ndev = min(_lib.device_count(), 8)
+    s, y = synthetic(200003, 2, 17)
+    eps2 = np.linspace(0.0, 0.02, len(s))
+    one = engine(s, y, eps2)
+    one.build_neighbors_grid(15)
+    tab = one.get_neighbors()
+    multi = _lib.Engine(list(range(ndev)))
+    multi.set_data(s, y, eps2)
+    multi.build_neighbors_grid(15)
+    assert multi.knn_used_grid() and np.array_equal(multi.get_neighbors(), tab)
+    assert np.array_equal(multi.get_neighbor_rows(99990, 100010), tab[99990:100010])
+    rng = np.random.default_rng(2)
+    K = 11
+    prm = np.stack([rng.uniform(0.5, 2, K), rng.uniform(3, 30, K), rng.uniform(0.01, 0.5, K), np.zeros(K)], 1)
+    for k in (1, 3, 11):
+        a, b = multi.loglik(1, prm[:k]), one.loglik(1, prm[:k])
+        np.testing.assert_allclose(a[:, :2], b[:, :2], rtol=1e-12)
+        assert np.array_equal(a[:, 2], b[:, 2])
+    np.testing.assert_allclose(multi.loglik_terms(1, *prm[0, :3])[:2], one.loglik(1, prm[0])[0][:2], rtol=1e-12)
+    B, F = multi.factors(1, prm[0], 99990, 100010)                    # rows that straddle two devices
+    B0, F0 = one.factors(1, prm[0], 99990, 100010)
+    assert np.array_equal(B, B0) and np.array_equal(F, F0)
+    y2 = np.cos(5 * y)
+    multi.set_y(y2); one.set_y(y2)
+    np.testing.assert_allclose(multi.loglik(1, prm[0])[0][:2], one.loglik(1, prm[0])[0][:2], rtol=1e-12)
+    multi.set_shard(1000, 150001); one.set_shard(1000, 150001)
+    multi.build_neighbors_grid(15)
+    np.testing.assert_allclose(multi.loglik(1, prm[0])[0][:2], one.loglik(1, prm[0])[0][:2], rtol=1e-12)
+    multi.set_shard(0, len(s)); multi.set_neighbors(tab)
+    want = {k: multi.loglik(1, prm[:k]) for k in (1, 5, 11)}
+    for it in range(1000):                                            # the fused exchange, generation after generation
+        k = (1, 5, 11)[it % 3]
+        assert np.array_equal(multi.loglik(1, prm[:k]), want[k]), (it, k)
+    multi.close()
+    # tiny inputs: more devices than rows leaves some devices with an empty shard
+    s3, y3 = synthetic(5, 2, 1)
+    tiny = _lib.Engine(list(range(ndev)))
+    tiny.set_data(s3, y3)
+    tiny.build_neighbors_grid(3)
+    st0 = orc.c_loglik(s3, y3, orc.c_knn_ordered(s3, 3), 0, *P0[:3])
+    np.testing.assert_allclose(tiny.loglik(0, P0)[0][:2], st0[:2], rtol=RTOL64)
+
+
+def test_class_on_all_devices_of_the_process():
+    """NNGP(t, y, eps, refType, m, cov) in a plain process uses every visible GPU (devices=None) -- skipped on a
+    1-GPU box; devices=<int> pins one.  Same table, same statistics, same predictions."""
+    _need_gpus(2)
+    import pyNNGP
+    from pynngp_b200 import Matern
+
+    s, y = synthetic(120000, 3, 23)
+    spec = Matern(1.5, **PARAMS)
+    every = pyNNGP.NNGP(s, y, 0.0, "S=T", 30, spec)
+    single = pyNNGP.NNGP(s, y, 0.0, "S=T", 30, spec, devices=0)
+    assert len(every.devices) == min(_lib.device_count(), 8) and single.devices == [0]
+    assert np.array_equal(every._table, single._table)
+    np.testing.assert_allclose(every.loglik_terms(), single.loglik_terms(), rtol=1e-12)
+    np.testing.assert_allclose(every.loglik_batch(np.array([[1.0, 6.0, 0.1], [1.5, 9.0, 0.2]])),
+                               single.loglik_batch(np.array([[1.0, 6.0, 0.1], [1.5, 9.0, 0.2]])), rtol=1e-12)
+    assert np.array_equal(every._Bsi(70000), single._Bsi(70000))
+    tn = np.random.default_rng(3).random((50, 3))
+    for a, b in zip(every.predict(tn), single.predict(tn)):
+        assert np.array_equal(a, b)
+    sub = pyNNGP.NNGP(s[:9000], y[:9000], 0.0, ("subset", 3000), 10, spec, seed=1)
+    sub1 = pyNNGP.NNGP(s[:9000], y[:9000], 0.0, ("subset", 3000), 10, spec, seed=1, devices=0)
+    np.testing.assert_allclose(sub.loglik_terms(), sub1.loglik_terms(), rtol=1e-12)
 
 
 def test_two_gpu_sharded_equals_single():

@@ -11,7 +11,7 @@ import numpy as np
 import pytest
 
 from oracle import nngp_oracle as orc
-from pynngp_b200.synthetic import synthetic
+from pynngp_b200.synthetic import CONFIGS, synthetic
 
 TIE_FREE = ["test_init_shape", "cfg1", "d2_m15", "d3_m30", "d1_m5", "d3_m32"]
 
@@ -267,3 +267,36 @@ def test_loglik_equals_product_of_gaussian_conditionals_scipy(kernel_id, D, m):
     np.testing.assert_allclose(orc.loglik_from_terms(slog, squad, n), want, rtol=1e-10)
     npo = orc.NumpyNNGP(s, y, tab, kernel_id, sigma2, phi, tau2, eps2=eps2)
     np.testing.assert_allclose(orc.loglik_from_terms(*npo.loglik_terms(), n), want, rtol=1e-10)
+
+
+def test_oracle_matches_extended_precision_known_answers(golden_dir):
+    """tests/golden/kat_cfg1.npz (made by make_kat.py): cfg1 on the unmodified reference's own neighbour sets,
+    every number evaluated in 80-bit extended precision with textbook formulas that share no code with the
+    oracle.  Both restatements (C and numpy) must reproduce the per-location C_N, c, C_ii, b_i, F_i, r_i of six
+    rows and the two halves of Q.  A simultaneous drift of oracle and kernels would show up here."""
+    k = np.load(os.path.join(golden_dir, "kat_cfg1.npz"))
+    g = np.load(os.path.join(golden_dir, "ns_cfg1.npz"))
+    c = CONFIGS["cfg1"]
+    s, y = synthetic(c["n"], c["D"], c["seed"])
+    tab, eps2, m = g["Ns"], k["eps2"], int(k["m"])
+    assert np.array_equal(tab, orc.c_knn_ordered(s, m))  # the reference's sets == the oracle's
+    prm = tuple(k["params"])
+    for kid in (0, 1):
+        slog, squad, bad = orc.c_loglik(s, y, tab, kid, *prm, eps2=eps2)
+        assert bad == 0
+        np.testing.assert_allclose([slog, squad], [k[f"k{kid}_sum_log_F"], k[f"k{kid}_sum_r2_over_F"]], rtol=1e-12)
+        npo = orc.NumpyNNGP(s, y, tab, kid, *prm, eps2=eps2)
+        np.testing.assert_allclose(npo.loglik_terms(), [k[f"k{kid}_sum_log_F"], k[f"k{kid}_sum_r2_over_F"]], rtol=1e-12)
+        CN, cc, cs = orc.c_cov_blocks(s, tab, kid, *prm, eps2=eps2)
+        B, F = orc.c_factors(s, y, tab, kid, *prm, eps2=eps2)
+        for i in k["rows"]:
+            np.testing.assert_allclose(CN[i], k[f"k{kid}_CN_{i}"], rtol=1e-14, atol=1e-300)
+            np.testing.assert_allclose(cc[i], k[f"k{kid}_c_{i}"], rtol=1e-14, atol=1e-300)
+            np.testing.assert_allclose(cs[i], k[f"k{kid}_Cii_{i}"], rtol=1e-15)
+            np.testing.assert_allclose(B[i], k[f"k{kid}_b_{i}"], rtol=0, atol=1e-11)
+            np.testing.assert_allclose(F[i], k[f"k{kid}_F_{i}"], rtol=1e-12)
+            p = int((tab[i] >= 0).sum())
+            np.testing.assert_allclose(npo._Bsi(i), k[f"k{kid}_b_{i}"][:p], rtol=0, atol=1e-11)
+            np.testing.assert_allclose(npo._Fsi(i), k[f"k{kid}_F_{i}"], rtol=1e-12)
+            r_i = y[i] - (B[i][:p] @ y[tab[i][:p]] if p else 0.0)
+            np.testing.assert_allclose(r_i, k[f"k{kid}_r_{i}"], rtol=1e-10, atol=1e-13)

@@ -21,7 +21,9 @@ dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 rank, world = dist.get_rank(), dist.get_world_size()
 s, y = synthetic(c["n"], c["D"], c["seed"])
 spec = Matern(1.5, **PARAMS)
-model = NNGP(s, y, 0.0, "S=T", c["m"], spec, device=local)          # sharded: knn split + MAX-assemble
+model = NNGP(s, y, 0.0, "S=T", c["m"], spec, devices=local)         # sharded: every rank searches and keeps its own rows
+lo, hi = model._shard
+assert model._engine.neighbor_window() == (lo, hi - lo)
 terms = model.loglik_terms()
 # the fused peer-memory exchange against the NCCL allreduce: same totals (summation order differs)
 peer = model._peer_ok
@@ -33,11 +35,19 @@ batch = model.loglik_batch(np.array([[1.0, 6.0, 0.1], [1.5, 9.0, 0.2], [0.7, 4.0
 allb = [None] * dist.get_world_size()
 dist.all_gather_object(allb, batch.tobytes())
 assert all(b == allb[0] for b in allb), "ranks disagree on the exchanged totals"
+# more parameter vectors than the exchange buffer holds (chunks), and 300 generations back to back
+from pynngp_b200.synthetic import sweep_params
+big = model.loglik_batch(sweep_params(200)[:, :3])
+for k in (0, 131, 199):
+    np.testing.assert_allclose(big[k], model.loglik_batch(sweep_params(200)[k:k + 1, :3])[0], rtol=1e-11)
+for it in range(300):
+    assert model.loglik_terms() == terms, it
+table_all = model.gather_table()                                        # collective: all_gather of the row blocks
 if rank == 0:
     e = _lib.Engine(local)                                              # single-GPU reference on rank 0
     e.set_data(s, y)
     e.build_neighbors(c["m"])
-    assert np.array_equal(e.get_neighbors(), model._table), "assembled neighbour table differs"
+    assert np.array_equal(e.get_neighbors(), table_all), "assembled neighbour table differs"
     one = e.loglik(1, np.array([PARAMS["sigma2"], PARAMS["phi"], PARAMS["tau2"], 0.0]))[0]
     np.testing.assert_allclose(terms, one[:2], rtol=1e-12)
     print(f"multi-gpu ok: world={world} n={c['n']} m={c['m']} D={c['D']} peer_exchange={peer} terms={terms} knn_s={model._timings['knn_s']:.3f}")
