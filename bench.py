@@ -16,6 +16,11 @@ host statistics out, every step); `roofline` is the fused kernel against the mea
 issue peak (and, secondary, the measured HBM peak); `cpu_baseline` is the C oracle on the host cores.
 `--impl reference` times the reference's CPU path (the oracle port: the reference has no likelihood
 implementation and no compiled sources) on a bounded sample with all host threads.
+
+`--gpus N` inside torchrun (WORLD_SIZE = N) is one process per GPU; `--gpus N` in a plain process runs the N GPUs
+through ONE multi-device handle (nngp_create_multi), timed by events around each device's kernel.
+Alongside cfg3 the line carries `detail.cfg4` (n = 1e7, m = 30, 3-D: the north_star's scaling target) and
+`parity` (the timed statistics against the oracle over all n rows).
 """
 from __future__ import annotations
 
@@ -103,23 +108,29 @@ class ClockSampler:
 
 
 def oracle_sample_rate(s, y, m, kid, threads, sample, min_seconds):
-    """Times the CPU oracle (oracle/nngp_oracle.c) on `sample` contiguous rows from the middle of the
-    ordering; returns (seconds per full-n evaluation, description)."""
+    """Times the CPU oracle (oracle/nngp_oracle.c) on `sample` rows strided over the upper three quarters of the
+    ordering (the reference arm has no GPU-built table, and the oracle's own exact search costs O(i) per row, so
+    the whole of n = 1e6 is out of reach on the host).  The sampled rows keep their true neighbour sets, spread
+    over all preceding rows, so the gathers miss the caches as they do in a full pass: they are appended as rows
+    n .. n+sample of a copy of the inputs and evaluated there.  Returns (seconds per full-n evaluation, description)."""
     from oracle import nngp_oracle as orc  # the checker, used here only as the timed CPU baseline
 
     n = len(s)
-    lo = n // 2
-    hi = min(n, lo + sample)
-    nbr = orc.c_knn_ordered(s, m, lo=lo, hi=hi, threads=threads)  # untimed setup of the sample's rows
+    sample = int(min(sample, max(1, n - n // 4)))
+    rows = np.unique(np.linspace(n // 4, n - 1, sample).astype(np.int64))
+    tab = orc.c_knn_rows(s, m, rows, threads=threads)  # untimed setup: the exact ordered search of the sampled rows
+    s2 = np.concatenate([s, s[rows]])
+    y2 = np.concatenate([y, y[rows]])
     reps, spent = 0, 0.0
     prm = (PARAMS["sigma2"], PARAMS["phi"], PARAMS["tau2"])
     while spent < min_seconds:
         t0 = time.perf_counter()
-        orc.c_loglik(s, y, nbr, kid, *prm, lo=lo, hi=hi, threads=threads)
+        orc.c_loglik_rows(s2, y2, tab, n, kid, *prm, threads=threads)
         spent += time.perf_counter() - t0
         reps += 1
-    per_loc = spent / (reps * (hi - lo))
-    return per_loc * n, f"{hi - lo} contiguous rows [{lo},{hi}) x {reps} reps, scaled to n={n}"
+    per_loc = spent / (reps * len(rows))
+    return per_loc * n, (f"{len(rows)} rows strided over [{n // 4},{n}) with their true neighbour sets x {reps} reps, scaled to n={n} "
+                         f"(extrapolated; {threads} threads)")
 
 
 def reference_stage1_timing(cfg, sizes=None):
@@ -155,7 +166,7 @@ def run_reference(args, cfg):
     if args.cpu_seconds is not None:
         per_step_budget = args.cpu_seconds
     for _ in range(args.warmup):
-        oracle_sample_rate(s[:200000], y[:200000], cfg["m"], kid, threads, 2048, 0.2)
+        oracle_sample_rate(s[:50000], y[:50000], cfg["m"], kid, threads, 512, 0.2)
     times, sample = [], ""
     for _ in range(args.steps):
         sec_per_eval, sample = oracle_sample_rate(s, y, cfg["m"], kid, threads, args.cpu_sample, per_step_budget)
@@ -167,7 +178,7 @@ def run_reference(args, cfg):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": workload_config(cfg, args.gpus),
-        "cpu_baseline": {"value": value, "unit": "evals/s", "cores": threads, "kind": "port", "sample": sample,
+        "cpu_baseline": {"value": value, "unit": "evals/s", "cores": threads, "kind": "port", "sample": sample, "extrapolated": True,
                          "stage1_reference": reference_stage1_timing(cfg)},
         "e2e": {"value": value, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "the reference (pyNNGP/nngp.py:73-96) has no likelihood implementation and no compiled sources; "
@@ -183,17 +194,22 @@ def workload_config(cfg, gpus):
             "sharding": f"contiguous ordering blocks x{gpus}", "l2": "flushed between timed steps (256 MiB write)"}
 
 
+def _stat_rel(a, b):
+    a, b = np.asarray(a, dtype=np.float64)[:2], np.asarray(b, dtype=np.float64)[:2]
+    return float(np.max(np.abs(a - b) / np.maximum(np.abs(b), 1e-300)))
+
+
 def run_ours(args, cfg):
     import torch
     import torch.distributed as dist
 
     from pynngp_b200 import NNGP, Matern, Exponential, _lib
-    from pynngp_b200.dist import DevicePtrView
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
-    if world != args.gpus:
+    single_process = world == 1 and args.gpus > 1  # ONE process, a multi-device handle (nngp_create_multi)
+    if world != args.gpus and not single_process:
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run")
     torch.cuda.set_device(local)
     if world > 1:
@@ -201,124 +217,170 @@ def run_ours(args, cfg):
         # the one JSON line and nothing else
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-
-    s, y = synthetic(cfg["n"], cfg["D"], cfg["seed"])
-    kid = KIDS[cfg["kernel"]]
-    spec = {"exponential": Exponential(**PARAMS), "matern32": Matern(1.5, **PARAMS), "matern52": Matern(2.5, **PARAMS)}[cfg["kernel"]]
-
-    # ---- setup (untimed, reported): upload + stage 1 through the public class -------------------
-    t0 = time.perf_counter()
-    model = NNGP(s, y, 0.0, "S=T", cfg["m"], spec, dtype=args.dtype, device=local)
-    torch.cuda.synchronize()
-    setup_s = time.perf_counter() - t0
-    eng = model._engine
-    knn_s = model._timings["knn_s"]
-
-    prm_host = np.array([[PARAMS["sigma2"], PARAMS["phi"], PARAMS["tau2"], 0.0]])
-    d_prm = torch.tensor(prm_host, dtype=torch.float64, device="cuda")
-    d_out = torch.zeros((1, 3), dtype=torch.float64, device="cuda")
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
-    stream = torch.cuda.Stream()  # a real stream: the C ABI treats NULL as 'the handle's own stream'
-    torch.cuda.set_stream(stream)
-
-    fused_exchange = world > 1 and model._peer_ok and not args.nccl_allreduce
-
-    def step_device():
-        if fused_exchange:  # kernel + sum over ranks through NVLink peer memory in one launch
-            eng.loglik_device_allreduce(kid, d_prm.data_ptr(), 1, d_out.data_ptr(), stream.cuda_stream)
-        else:
-            eng.loglik_device(kid, d_prm.data_ptr(), 1, d_out.data_ptr(), stream.cuda_stream)
-            if world > 1:
-                dist.all_reduce(d_out)
+        warm = torch.zeros(1, device="cuda")
+        dist.all_reduce(warm)  # the communicator is created here, outside every timed or reported region
+        torch.cuda.synchronize()
+    ngpu = args.gpus
+    devices = list(range(ngpu)) if single_process else local
 
     def barrier():
         if world > 1:
             dist.barrier()
-        torch.cuda.synchronize()
+        for d in (range(ngpu) if single_process else (local,)):
+            torch.cuda.synchronize(d)
 
-    for _ in range(max(args.warmup, 3)):
-        flush.zero_()
-        step_device()
-    barrier()
-    ref_stats = d_out.cpu().numpy().copy()
+    def max_over_ranks(v):
+        t = torch.tensor([float(v)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
 
-    # ---- device-timed: K steps, each bracketed by CUDA events on the launching stream -------------
+    flushes = [torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{d}") for d in (range(ngpu) if single_process else (local,))]
+
+    def flush_l2():
+        for f in flushes:
+            f.zero_()
+        if single_process:  # the engine's own streams are not torch's: order the flush before the evaluation
+            for d in range(ngpu):
+                torch.cuda.synchronize(d)
+
+    def measure(c, steps, want_extras):
+        """Builds the model of configuration c through the public class and times `steps` evaluations."""
+        s, y = synthetic(c["n"], c["D"], c["seed"])
+        kid = KIDS[c["kernel"]]
+        spec = {"exponential": Exponential(**PARAMS), "matern32": Matern(1.5, **PARAMS), "matern52": Matern(2.5, **PARAMS)}[c["kernel"]]
+        barrier()
+        t0 = time.perf_counter()
+        model = NNGP(s, y, 0.0, "S=T", c["m"], spec, dtype=args.dtype, devices=devices)
+        barrier()
+        out = {"s": s, "y": y, "kid": kid, "spec": spec, "model": model, "setup_s": max_over_ranks(time.perf_counter() - t0),
+               "knn_s": max_over_ranks(model._timings["knn_s"])}
+        eng = model._engine
+        prm_host = np.array([[PARAMS["sigma2"], PARAMS["phi"], PARAMS["tau2"], 0.0]])
+        fused_exchange = world > 1 and model._peer_ok and not args.nccl_allreduce
+        out["fused_exchange"] = fused_exchange
+        if single_process:
+            eng.set_timing(True)
+
+            def step():
+                return eng.loglik(kid, prm_host)[0]
+
+            for _ in range(max(args.warmup, 3)):
+                flush_l2()
+                ref = step()
+            times = []
+            launches0 = eng.launch_count()
+            tw0 = time.time()
+            for _ in range(steps):
+                flush_l2()
+                step()
+                times.append(eng.last_eval_ms())  # events around each device's kernel, max over the devices
+            tw1 = time.time()
+            out.update(stats=np.asarray(ref), step_ms=np.array(times), launches=eng.launch_count() - launches0, wall=(tw0, tw1),
+                       kern_ms=None, warm_ms=None)
+            return out
+        d_prm = torch.tensor(prm_host, dtype=torch.float64, device="cuda")
+        d_out = torch.zeros((1, 3), dtype=torch.float64, device="cuda")
+        stream = torch.cuda.Stream()  # a real stream: the C ABI treats NULL as 'the handle's own stream'
+        torch.cuda.set_stream(stream)
+
+        def step_device(nccl=False):
+            if fused_exchange and not nccl:  # kernel + sum over ranks through NVLink peer memory in one launch
+                eng.loglik_device_allreduce(kid, d_prm.data_ptr(), 1, d_out.data_ptr(), stream.cuda_stream)
+            else:
+                eng.loglik_device(kid, d_prm.data_ptr(), 1, d_out.data_ptr(), stream.cuda_stream)
+                if world > 1:
+                    dist.all_reduce(d_out)
+
+        for _ in range(max(args.warmup, 3)):
+            flush_l2()
+            step_device()
+        barrier()
+        out["stats"] = d_out.cpu().numpy()[0].copy()
+        if world > 1:  # the same numbers through the other exchange (summation order differs)
+            step_device(nccl=fused_exchange)
+            barrier()
+            out["stats_other_exchange"] = d_out.cpu().numpy()[0].copy()
+        launches0 = eng.launch_count()
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        barrier()
+        tw0 = time.time()
+        for a, b in evs:
+            flush_l2()
+            a.record(stream)
+            step_device()
+            b.record(stream)
+        barrier()
+        tw1 = time.time()
+        out.update(launches=eng.launch_count() - launches0, wall=(tw0, tw1),
+                   step_ms=np.array([a.elapsed_time(b) for a, b in evs]))
+        # kernel-only duration for the roofline (no exchange, flushed L2, per-launch events)
+        kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        for ka, kb in kev:
+            flush_l2()
+            ka.record(stream)
+            eng.loglik_device(kid, d_prm.data_ptr(), 1, d_out.data_ptr(), stream.cuda_stream)
+            kb.record(stream)
+        barrier()
+        out["kern_ms"] = float(np.median([ka.elapsed_time(kb) for ka, kb in kev]))
+        if want_extras:
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream)
+            for _ in range(steps):
+                step_device()
+            b.record(stream)
+            barrier()
+            out["warm_ms"] = a.elapsed_time(b) / steps
+            out["stream"], out["d_bufs"] = stream, (d_prm, d_out)
+        return out
+
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
         time.sleep(0.3)
-    launches0 = eng.launch_count()
-    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    barrier()
-    tw0 = time.time()
-    for a, b in evs:
-        flush.zero_()
-        a.record(stream)
-        step_device()
-        b.record(stream)
-    barrier()
-    tw1 = time.time()
-    launches = eng.launch_count() - launches0
-    step_ms = np.array([a.elapsed_time(b) for a, b in evs])
-    total_ms = torch.tensor([float(step_ms.sum())], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
-    total_ms = float(total_ms.item())
-    clocks = sampler.stop(tw0, tw1) if rank == 0 else None
-
-    # warm-L2 variant (no flush), reported in config for context
-    barrier()
-    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    a.record(stream)
-    for _ in range(args.steps):
-        step_device()
-    b.record(stream)
-    barrier()
-    warm_ms = a.elapsed_time(b) / args.steps
-
-    # kernel-only duration for the roofline (no allreduce, flushed L2, per-launch events)
-    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    for ka, kb in kev:
-        flush.zero_()
-        ka.record(stream)
-        eng.loglik_device(kid, d_prm.data_ptr(), 1, d_out.data_ptr(), stream.cuda_stream)
-        kb.record(stream)
-    barrier()
-    kern_ms = float(np.mean([ka.elapsed_time(kb) for ka, kb in kev]))
+    M = measure(cfg, args.steps, True)
+    clocks = sampler.stop(*M["wall"]) if rank == 0 else None
+    model, eng, s, y, kid = M["model"], M["model"]._engine, M["s"], M["y"], M["kid"]
+    # value: the median step (SURVEY 8 d1), the slowest rank's; the mean is kept beside it
+    ms_per_step = max_over_ranks(float(np.median(M["step_ms"])))
+    ms_per_step_mean = max_over_ranks(float(np.mean(M["step_ms"])))
+    kern_ms = M["kern_ms"] if M["kern_ms"] is not None else ms_per_step
 
     # ---- cfg5: a sweep of K parameter vectors in one launch (pair distances shared by the vectors) ----
     from pynngp_b200.synthetic import sweep_params
 
     Ks = 64
-    d_prmK = torch.tensor(sweep_params(Ks), dtype=torch.float64, device="cuda")
-    d_outK = torch.zeros((Ks, 3), dtype=torch.float64, device="cuda")
+    sweep = None
+    if not single_process:
+        stream = M["stream"]
+        d_prmK = torch.tensor(sweep_params(Ks), dtype=torch.float64, device="cuda")
+        d_outK = torch.zeros((Ks, 3), dtype=torch.float64, device="cuda")
 
-    def sweep_device():
-        if fused_exchange:
-            eng.loglik_device_allreduce(kid, d_prmK.data_ptr(), Ks, d_outK.data_ptr(), stream.cuda_stream)
-        else:
-            eng.loglik_device(kid, d_prmK.data_ptr(), Ks, d_outK.data_ptr(), stream.cuda_stream)
-            if world > 1:
-                dist.all_reduce(d_outK)
+        def sweep_device():
+            if M["fused_exchange"]:
+                eng.loglik_device_allreduce(kid, d_prmK.data_ptr(), Ks, d_outK.data_ptr(), stream.cuda_stream)
+            else:
+                eng.loglik_device(kid, d_prmK.data_ptr(), Ks, d_outK.data_ptr(), stream.cuda_stream)
+                if world > 1:
+                    dist.all_reduce(d_outK)
 
-    sweep_device()
-    barrier()
-    sw = []
-    for _ in range(3):
-        flush.zero_()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record(stream)
         sweep_device()
-        b.record(stream)
         barrier()
-        sw.append(a.elapsed_time(b))
-    sweep_t = torch.tensor([float(np.mean(sw))], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(sweep_t, op=dist.ReduceOp.MAX)
-    sweep_ms = float(sweep_t.item())
+        sw = []
+        for _ in range(3):
+            flush_l2()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream)
+            sweep_device()
+            b.record(stream)
+            barrier()
+            sw.append(a.elapsed_time(b))
+        sweep_ms = max_over_ranks(float(np.median(sw)))
+        sweep = {"K": Ks, "ms_per_launch": sweep_ms, "ms_per_eval": sweep_ms / Ks, "evals_per_s": 1e3 * Ks / sweep_ms,
+                 "what": "K parameter vectors (synthetic.sweep_params) in ONE launch: distances built once per location"}
 
-    # ---- end to end through the public API (host params in, host stats out, every step) ----------
-    for _ in range(3):
+    # ---- end to end through the public API (host parameters in, host statistics out, every step) ----------
+    for _ in range(5):
         model.loglik_terms()
     barrier()
     t0 = time.perf_counter()
@@ -326,11 +388,7 @@ def run_ours(args, cfg):
         e2e_terms = model.loglik_terms(PARAMS["sigma2"], PARAMS["phi"], PARAMS["tau2"])
     if world > 1:
         dist.barrier()
-    e2e_s = time.perf_counter() - t0
-    e2e_t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
-    e2e_s = float(e2e_t.item())
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
 
     # ---- the same with the response re-uploaded every step (a sampler that updates the field between
     #      evaluations: nngp_set_y, n doubles host -> device, then the evaluation) -------------------------
@@ -344,34 +402,67 @@ def run_ours(args, cfg):
         model.loglik_terms(PARAMS["sigma2"], PARAMS["phi"], PARAMS["tau2"])
     if world > 1:
         dist.barrier()
-    e2e_y_t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(e2e_y_t, op=dist.ReduceOp.MAX)
-    e2e_y_s = float(e2e_y_t.item())
+    e2e_y_s = max_over_ranks(time.perf_counter() - t0)
     eng.set_y(y_alt[0])
 
     # ---- cold path through the public API: host arrays -> upload -> stage 1 -> one evaluation ----
-    cold = []
+    cold, cold_knn = [], []
     for _ in range(2):
         barrier()
         t0 = time.perf_counter()
-        mdl = NNGP(s, y, 0.0, "S=T", cfg["m"], spec, dtype=args.dtype, device=local)
+        mdl = NNGP(s, y, 0.0, "S=T", cfg["m"], M["spec"], dtype=args.dtype, devices=devices)
         cold_terms = mdl.loglik_terms()
         cold.append(time.perf_counter() - t0)
-        cold_knn = mdl._timings["knn_s"]
+        cold_knn.append(mdl._timings["knn_s"])
+        mdl.close()
         del mdl
-    cold_t = torch.tensor([min(cold)], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(cold_t, op=dist.ReduceOp.MAX)
-    cold_s = float(cold_t.item())
+    cold_s = max_over_ranks(min(cold))
+    cold_knn_s = max_over_ranks(min(cold_knn))
+
+    # ---- BASELINE.json configs[3] (n = 1e7, m = 30, 3-D): the north_star's scaling target, at every N ------
+    cfg4 = None
+    if args.config == "cfg3" and not args.no_cfg4 and args.dtype == "float64":
+        c4 = CONFIGS["cfg4"]
+        M4 = measure(c4, 10, False)
+        ms4 = max_over_ranks(float(np.median(M4["step_ms"])))
+        k4 = max_over_ranks(M4["kern_ms"]) if M4["kern_ms"] is not None else ms4
+        cfg4 = {"workload": workload_config(c4, ngpu)["workload"], "ms_per_eval": ms4, "evals_per_s": 1e3 / ms4, "kernel_ms": k4,
+                "knn_build_s": M4["knn_s"], "setup_s": M4["setup_s"], "steps": 10, "stats": M4["stats"].tolist(),
+                "exchange_rel_diff": _stat_rel(M4["stats_other_exchange"], M4["stats"]) if "stats_other_exchange" in M4 else None}
+        if rank == 0:
+            e4 = M4["model"]._engine
+            nloc4 = (M4["model"]._shard[1] - M4["model"]._shard[0]) if not single_process else -(-c4["n"] // ngpu)
+            ipl4 = fp64_instr_per_location(c4["m"], c4["D"], c4["kernel"])
+            peak4 = e4.measure_fma_peak(args.dtype, 4096)
+            cfg4["roofline_frac"] = nloc4 * ipl4 / (k4 * 1e-3) / peak4
+            # parity of the numbers just timed: a 20 000-row slab of rank 0's shard against the oracle
+            from oracle import nngp_oracle as orc  # the checker
+
+            lo4, hi4 = 100000, 120000
+            rows4 = e4.get_neighbor_rows(lo4, hi4)
+            want4 = orc.c_loglik_rows(M4["s"], M4["y"], rows4, lo4, KIDS[c4["kernel"]], PARAMS["sigma2"], PARAMS["phi"], PARAMS["tau2"],
+                                      threads=os.cpu_count() or 1)
+            one4 = _lib.Engine(local, args.dtype)
+            one4.set_data(M4["s"][:hi4], M4["y"][:hi4])
+            pad = np.full((hi4, c4["m"]), -1, dtype=np.int32)
+            pad[lo4:hi4] = rows4
+            one4.set_neighbors(pad)
+            one4.set_shard(lo4, hi4)
+            got4 = one4.loglik(KIDS[c4["kernel"]], np.array([PARAMS["sigma2"], PARAMS["phi"], PARAMS["tau2"], 0.0]))[0]
+            one4.close()
+            cfg4["parity"] = {"slab_rows": [lo4, hi4], "rel_err_vs_oracle": _stat_rel(got4, want4),
+                              "what": "the timed table's rows [lo, hi) evaluated by the fused kernel against oracle/nngp_oracle.c"}
+        M4["model"].close()
+        del M4
 
     if rank != 0:
         if world > 1:
+            dist.barrier()
             dist.destroy_process_group()
         return
 
     # ---- roofline of the fused kernel --------------------------------------------------------------
-    nloc = model._shard[1] - model._shard[0]
+    nloc = (model._shard[1] - model._shard[0]) if not single_process else -(-cfg["n"] // ngpu)
     ipl = fp64_instr_per_location(cfg["m"], cfg["D"], cfg["kernel"])
     peak_instr = eng.measure_fma_peak(args.dtype, 4096)
     achieved_tflops = nloc * ipl * 2 / (kern_ms * 1e-3) / 1e12
@@ -383,14 +474,17 @@ def run_ours(args, cfg):
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     hbm_ach = nloc * hbm_bytes_per_location(cfg["m"], cfg["D"]) / (kern_ms * 1e-3) / 1e9
-    traffic = None
+    traffic, traffic_source = None, None
     tr_path = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tr_path) and args.config == "cfg3" and world == 1 and args.dtype == "float64":
-        traffic = json.load(open(tr_path)).get("fused_dram_bytes_per_launch")  # ncu capture of this very workload
+    if os.path.exists(tr_path) and args.config == "cfg3" and ngpu == 1 and args.dtype == "float64":
+        tr = json.load(open(tr_path))
+        traffic = tr.get("fused_dram_bytes_per_launch")
+        traffic_source = ("constant read from profiles/traffic.json: dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` "
+                          f"capture of this workload's kernel ({tr.get('source', 'see profiles/README.md')}); not measured in this run")
     roofline = {
         "bound": "fp64" if args.dtype == "float64" else "fp32",
         "achieved": achieved_tflops, "peak": peak_tflops, "unit": "TFLOP/s", "frac": achieved_tflops / peak_tflops,
-        "traffic": traffic,
+        "traffic": traffic, "traffic_source": traffic_source,
         "kernel": "nngp_fused::fused_loglik_kernel", "kernel_ms": kern_ms,
         "algorithmic_instr_per_location": ipl, "locations_per_launch": nloc,
         "peak_source": "measured here: register-resident FMA chains, nngp_measure_fma_peak (no vector-pipe figure in MEASURED_PEAKS.json)",
@@ -399,44 +493,72 @@ def run_ours(args, cfg):
                 "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"},
     }
 
-    # ---- CPU baseline (the oracle port) on this host ---------------------------------------------
+    # ---- parity of the numbers being timed + CPU baseline: the oracle over ALL n rows on this host -------------
+    from oracle import nngp_oracle as orc  # the checker; also the timed CPU baseline below
+
     threads = os.cpu_count() or 1
-    sec_cpu, sample = oracle_sample_rate(s, y, cfg["m"], kid, threads, args.cpu_sample, 10.0)
-    cpu_baseline = {"value": 1.0 / sec_cpu, "unit": "evals/s", "cores": threads, "kind": "port", "sample": sample}
+    table = model._table  # one rank alone may read it (a rank of a sharded run searches the missing rows itself)
+    prm = (PARAMS["sigma2"], PARAMS["phi"], PARAMS["tau2"])
+    reps, spent, want = 0, 0.0, None
+    budget = args.cpu_seconds if args.cpu_seconds is not None else 10.0
+    while spent < budget or reps == 0:
+        t0 = time.perf_counter()
+        want = orc.c_loglik(s, y, table, kid, *prm, threads=threads)
+        spent += time.perf_counter() - t0
+        reps += 1
+    parity = {"rows": [0, int(cfg["n"])], "rel_err_vs_oracle": _stat_rel(M["stats"], want), "n_bad": [float(M["stats"][2]), float(want[2])],
+              "e2e_rel_err_vs_oracle": _stat_rel(e2e_terms, want),
+              "tolerance": 1e-10 if args.dtype == "float64" else 1e-4,
+              "exchange_rel_diff": _stat_rel(M["stats_other_exchange"], M["stats"]) if "stats_other_exchange" in M else None,
+              "what": "the statistics of the timed evaluations (all n rows, summed over the ranks) against oracle/nngp_oracle.c on the "
+                      "same table; exchange_rel_diff = fused peer-memory exchange vs NCCL all_reduce of the same launch"}
+    limits = None
+    try:
+        from threadpoolctl import threadpool_info
+
+        limits = [{k: d.get(k) for k in ("user_api", "internal_api", "num_threads")} for d in threadpool_info()]
+    except Exception:
+        pass
+    cpu_baseline = {"value": reps / spent, "unit": "evals/s", "cores": threads, "kind": "port", "extrapolated": False,
+                    "sample": f"all {cfg['n']} rows x {reps} full evaluations ({spent:.1f} s) of oracle/nngp_oracle.c, {threads} threads "
+                              "(ThreadPoolExecutor over row chunks; no BLAS inside)",
+                    "os_cpu_count": os.cpu_count(), "threadpoolctl": limits}
     try:
         cpu_baseline["stage1_reference"] = reference_stage1_timing(cfg)
-        cpu_baseline["stage1_reference"]["ours_seconds_at_workload_n"] = knn_s
+        cpu_baseline["stage1_reference"]["ours_seconds_at_workload_n"] = M["knn_s"]
     except Exception as exc:  # scikit-learn missing on the host: the likelihood baseline above still stands
         cpu_baseline["stage1_reference"] = {"unavailable": repr(exc)}
 
-    # parity spot check on the very numbers being timed (cheap: the sample's rows)
-    ms_per_step = total_ms / args.steps
-    cfgd = workload_config(cfg, world)
-    cfgd["sweep_cfg5"] = {"K": Ks, "ms_per_launch": sweep_ms, "ms_per_eval": sweep_ms / Ks, "evals_per_s": 1e3 * Ks / sweep_ms,
-                          "what": "K parameter vectors (synthetic.sweep_params) in ONE launch: distances built once per location"}
-    cfgd["exchange"] = ("none (1 GPU)" if world == 1 else
-                        "fused into the kernel: P2P stores over NVLink peer memory (CUDA IPC), no NCCL call" if fused_exchange
-                        else "NCCL all_reduce of 3 doubles after the kernel")
-    cfgd.update({"setup_s": setup_s, "knn_build_s": knn_s, "knn_algo": "grid" if eng.knn_used_grid() else "brute",
-                 "cold_e2e": {"ms": cold_s * 1e3, "knn_ms": cold_knn * 1e3, "h2d_bytes": int(cfg["n"]) * 32, "d2h_bytes": 24,
-                              "what": "pyNNGP.NNGP(t, y, eps, 'S=T', m, cov) from host arrays (upload + stage 1) + one "
-                                      "loglik_terms(); best of 2", "stats": list(cold_terms)}, "warm_l2_ms_per_step": warm_ms, "stats": ref_stats[0].tolist(),
-                 "e2e_stats": list(e2e_terms),
-                 "e2e_y_upload": {"value": args.steps / e2e_y_s, "unit": "evals/s", "h2d_bytes_per_step": 8 * int(cfg["n"]) + 32,
-                                  "d2h_bytes_per_step": 24, "what": "nngp_set_y (the whole response, pageable host memory) + "
-                                  "loglik_terms() every step"}})
+    exchange = ("none (1 GPU)" if ngpu == 1 else
+                "ONE process, multi-device handle: per-device launcher threads, sum fused into the kernels' tails over peer memory" if single_process else
+                "fused into the kernel: P2P stores over NVLink peer memory (CUDA IPC), no NCCL call" if M["fused_exchange"]
+                else "NCCL all_reduce of 3 doubles after the kernel")
+    detail = {"exchange": exchange, "setup_s": M["setup_s"], "knn_build_s": M["knn_s"], "knn_algo": "grid" if eng.knn_used_grid() else "brute",
+              "ms_per_step_mean": ms_per_step_mean, "ms_per_step_min": float(np.min(M["step_ms"])), "warm_l2_ms_per_step": M["warm_ms"],
+              "stats": M["stats"].tolist(), "e2e_stats": list(e2e_terms), "sweep_cfg5": sweep,
+              "cold_e2e": {"ms": cold_s * 1e3, "knn_ms": cold_knn_s * 1e3, "h2d_bytes": int(cfg["n"]) * 8 * (cfg["D"] + 1), "d2h_bytes": 48,
+                           "what": "pyNNGP.NNGP(t, y, eps, 'S=T', m, cov) from host arrays (upload + stage 1) + one "
+                                   "loglik_terms(); best of 2", "stats": list(cold_terms)},
+              "e2e_y_upload": {"value": args.steps / e2e_y_s, "unit": "evals/s", "h2d_bytes_per_step": 8 * int(cfg["n"]) + 32,
+                               "d2h_bytes_per_step": 48, "what": "nngp_set_y (the whole response, pageable host memory) + "
+                               "loglik_terms() every step"},
+              "cfg4": cfg4}
     line = {
-        "metric": METRIC, "value": 1e3 / ms_per_step, "unit": "evals/s", "n_gpus": world, "steps": args.steps,
+        "metric": METRIC, "value": 1e3 / ms_per_step, "unit": "evals/s", "n_gpus": ngpu, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
-        "vs_baseline": None, "dtype": "f64" if args.dtype == "float64" else "f32", "data": "synthetic", "config": cfgd,
+        "vs_baseline": None, "dtype": "f64" if args.dtype == "float64" else "f32", "data": "synthetic",
+        "config": workload_config(cfg, ngpu), "value_is": "median step, slowest rank",
         "clocks": clocks,
-        "e2e": {"value": args.steps / e2e_s, "unit": "evals/s", "h2d_bytes_per_step": 32, "d2h_bytes_per_step": 24,
-                "api": "pyNNGP.NNGP.loglik_terms(sigma2, phi, tau2)"},
-        "gpu_launches": int(launches),
-        "roofline": roofline, "cpu_baseline": cpu_baseline,
+        "e2e": {"value": args.steps / e2e_s, "unit": "evals/s", "h2d_bytes_per_step": 32, "d2h_bytes_per_step": 48,
+                "api": "pyNNGP.NNGP.loglik_terms(sigma2, phi, tau2)",
+                "transport": "parameters: 32 bytes by value in the kernel arguments; statistics: 3 stamped 16-byte lines written by the "
+                             "kernel's last block into mapped pinned host memory and polled by the caller"},
+        "gpu_launches": int(M["launches"]),
+        "roofline": roofline, "cpu_baseline": cpu_baseline, "parity": parity, "detail": detail,
     }
     print(json.dumps(line), flush=True)
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 
@@ -451,6 +573,7 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=16384)
     ap.add_argument("--cpu-seconds", type=float, default=None, help="--impl reference: seconds of CPU work per step (default: 120 s over all steps, at most 20 s each)")
     ap.add_argument("--nccl-allreduce", action="store_true", help="multi-GPU: sum the statistics with NCCL instead of the fused peer-memory exchange")
+    ap.add_argument("--no-cfg4", action="store_true", help="skip the n = 1e7 block (BASELINE.json configs[3]) that rides along with cfg3")
     args = ap.parse_args()
     cfg = CONFIGS[args.config]
     if args.impl == "reference":

@@ -189,6 +189,12 @@ int nngp_cov_blocks(nngp_handle *h, int kernel_id, const double *params, int64_t
  * FP64 (dtype NNGP_F64) or FP32 FMA peak of the device in thread-instructions per second
  * (register-resident dependent-chain microbenchmark, `iters` FMAs per thread). */
 int64_t nngp_launch_count(const nngp_handle *h);
+/* Device-side timing of the evaluation kernels for a bench: with timing on, every evaluation launch is
+ * bracketed by CUDA events on its stream; nngp_last_eval_ms waits for the last one and returns its duration
+ * (for a multi-device handle the maximum over the devices -- each kernel's tail includes the wait for its
+ * peers, so this is the device time of the whole exchange-terminated step). */
+int nngp_set_timing(nngp_handle *h, int on);
+int nngp_last_eval_ms(nngp_handle *h, double *ms);
 int nngp_measure_fma_peak(nngp_handle *h, int dtype, int iters, double *instr_per_s);
 
 #ifdef __cplusplus

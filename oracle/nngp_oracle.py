@@ -261,6 +261,25 @@ def c_knn_ordered(s, m, lo=0, hi=None, threads=1):
     return out
 
 
+def c_knn_rows(s, m, rows, threads=1):
+    """(len(rows), m) int32: the neighbour sets of the listed rows only (each an exact O(i) scan); nothing of
+    size n x m is allocated -- the C routine is handed the address row 0 of a full table would have."""
+    lib = _load()
+    s, _, _, _ = _prep(s)
+    n, D = s.shape
+    rows = np.asarray(rows, dtype=np.int64)
+    out = np.full((len(rows), m), -1, dtype=np.int32)
+
+    def one(k):
+        i = int(rows[k])
+        base = ctypes.cast(out.ctypes.data + (k - i) * m * 4, ctypes.POINTER(ctypes.c_int32))
+        lib.oracle_knn_ordered(_dp(s), n, D, m, i, i + 1, base)
+
+    with ThreadPoolExecutor(max(threads, 1)) as ex:
+        list(ex.map(one, range(len(rows))))
+    return out
+
+
 def c_loglik(s, y, nbr, kernel_id, sigma2, phi, tau2, eps2=None, lo=0, hi=None, threads=1):
     """(sum log F, sum r^2/F, n_bad) over rows [lo, hi)."""
     lib = _load()
@@ -280,6 +299,27 @@ def c_loglik(s, y, nbr, kernel_id, sigma2, phi, tau2, eps2=None, lo=0, hi=None, 
         return tuple(one((lo, hi)))
     with ThreadPoolExecutor(threads) as ex:
         parts = list(ex.map(one, _chunks(lo, hi, threads)))
+    return tuple(np.sum(parts, axis=0))
+
+
+def c_loglik_rows(s, y, nbr_rows, row0, kernel_id, sigma2, phi, tau2, eps2=None, threads=1):
+    """c_loglik over rows [row0, row0 + len(nbr_rows)) when only those rows of the table are at hand (a slab of
+    a table too large to hold whole, e.g. n = 1e7): the C routine indexes the table by absolute row, so it is
+    handed the address row 0 would have."""
+    lib = _load()
+    s, y, eps2, nbr_rows = _prep(s, y, eps2, nbr_rows)
+    n, D = s.shape
+    cnt, m = nbr_rows.shape
+    params = np.array([sigma2, phi, tau2, 0.0], dtype=np.float64)
+    base = ctypes.cast(nbr_rows.ctypes.data - int(row0) * m * 4, ctypes.POINTER(ctypes.c_int32))
+
+    def one(ab):
+        out = np.zeros(3, dtype=np.float64)
+        lib.oracle_loglik(_dp(s), _dp(y), _dp(eps2), base, n, D, m, kernel_id, _dp(params), ab[0], ab[1], _dp(out))
+        return out
+
+    with ThreadPoolExecutor(max(threads, 1)) as ex:
+        parts = list(ex.map(one, _chunks(row0, row0 + cnt, max(threads, 1))))
     return tuple(np.sum(parts, axis=0))
 
 

@@ -60,6 +60,8 @@ SIGNATURES = {
     "nngp_factors": (ctypes.c_int, [_handle_p, ctypes.c_int, _c_double_p, ctypes.c_int64, ctypes.c_int64, _c_double_p, _c_double_p]),
     "nngp_cov_blocks": (ctypes.c_int, [_handle_p, ctypes.c_int, _c_double_p, ctypes.c_int64, ctypes.c_int64, _c_double_p, _c_double_p, _c_double_p]),
     "nngp_launch_count": (ctypes.c_int64, [_handle_p]),
+    "nngp_set_timing": (ctypes.c_int, [_handle_p, ctypes.c_int]),
+    "nngp_last_eval_ms": (ctypes.c_int, [_handle_p, _c_double_p]),
     "nngp_measure_fma_peak": (ctypes.c_int, [_handle_p, ctypes.c_int, ctypes.c_int, _c_double_p]),
 }
 
@@ -319,6 +321,14 @@ class Engine:
     # -- introspection -----------------------------------------------------------------------------
     def launch_count(self):
         return int(self._lib.nngp_launch_count(self._h))
+
+    def set_timing(self, on=True):
+        self._check(self._lib.nngp_set_timing(self._h, 1 if on else 0), "nngp_set_timing")
+
+    def last_eval_ms(self):
+        v = ctypes.c_double(0.0)
+        self._check(self._lib.nngp_last_eval_ms(self._h, ctypes.byref(v)), "nngp_last_eval_ms")
+        return v.value
 
     def measure_fma_peak(self, dtype="float64", iters=4096):
         v = ctypes.c_double(0.0)

@@ -178,7 +178,9 @@ int launch_eval(nngp_handle *h, int kernel_id, const double *d_params, const dou
     a.partials = h->d_partials; a.counters = h->d_counters; a.out = d_out; a.hout = hout; a.seq = seq;
     a.emit = 0; a.exp2tab = h->d_exp2tab; a.K = K;
     if (px) a.px = *px;
+    if (h->timing) CUDA_TRY(h, cudaEventRecord(h->ev0, st));
     CUDA_TRY(h, family_launch(h->dtype, kernel_id, h->m, h->D, a, K, grid, st));
+    if (h->timing) CUDA_TRY(h, cudaEventRecord(h->ev1, st));
     ++h->launches;
     return NNGP_OK;
 }
@@ -414,6 +416,8 @@ void nngp_destroy(nngp_handle *h)
     free_dev(h->xbuf);
     if (h->h_stage) cudaFreeHost(h->h_stage);
     if (h->h_out) cudaFreeHost(h->h_out);
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
 }
@@ -971,6 +975,49 @@ int nngp_cov_blocks(nngp_handle *h, int kernel_id, const double *params, int64_t
     if (!h) return fail(nullptr, NNGP_EINVAL, "null handle");
     if (!params) return fail(h, NNGP_EINVAL, "params must not be NULL");
     return run_emit(h, kernel_id, params, i0, i1, nullptr, nullptr, CN, cc, cs);
+}
+
+int nngp_set_timing(nngp_handle *h, int on)
+{
+    if (!h) return fail(nullptr, NNGP_EINVAL, "null handle");
+    if (is_group(h)) {
+        for (nngp_handle *s : h->group->subs) {
+            const int rc = nngp_set_timing(s, on);
+            if (rc) { h->err = s->err; return rc; }
+        }
+        return NNGP_OK;
+    }
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    if (on && !h->ev0) {
+        CUDA_TRY(h, cudaEventCreate(&h->ev0));
+        CUDA_TRY(h, cudaEventCreate(&h->ev1));
+    }
+    h->timing = on != 0;
+    return NNGP_OK;
+}
+
+int nngp_last_eval_ms(nngp_handle *h, double *ms)
+{
+    if (!h || !ms) return fail(h, NNGP_EINVAL, "null argument");
+    if (is_group(h)) {
+        double worst = 0.0;
+        for (nngp_handle *s : h->group->subs) {
+            if (s->hi == s->lo) continue;
+            double v = 0.0;
+            const int rc = nngp_last_eval_ms(s, &v);
+            if (rc) { h->err = s->err; return rc; }
+            worst = std::max(worst, v);
+        }
+        *ms = worst;
+        return NNGP_OK;
+    }
+    if (!h->timing || !h->ev1) return fail(h, NNGP_ESTATE, "timing is off (nngp_set_timing)");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    CUDA_TRY(h, cudaEventSynchronize(h->ev1));
+    float f = 0.f;
+    CUDA_TRY(h, cudaEventElapsedTime(&f, h->ev0, h->ev1));
+    *ms = double(f);
+    return NNGP_OK;
 }
 
 int64_t nngp_launch_count(const nngp_handle *h)

@@ -88,6 +88,9 @@ struct nngp_handle {
 
     int64_t launches = 0;
     std::string err;
+    // optional device-side timing of the evaluation launches (nngp_set_timing): events around the kernel
+    bool timing = false;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 
     // multi-device handle (nngp_create_multi): one sub-handle per device, driven by worker threads
     struct nngp_group *group = nullptr;
