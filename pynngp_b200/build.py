@@ -49,17 +49,12 @@ def _stale(target, deps):
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def _dev_defines():
-    """Development-only preprocessor defines (NNGP_DEV_DEFINES="NNGP_TUNE,NNGP_TIMELINE"); empty for the product."""
-    return [f"-D{d.strip()}=1" for d in os.environ.get("NNGP_DEV_DEFINES", "").split(",") if d.strip()]
-
-
-def _compile(src, verbose):
-    obj = os.path.join(OBJ_DIR, src.replace(".cu", ".o"))
+def _compile(src, verbose, obj_dir=OBJ_DIR, defines=()):
+    obj = os.path.join(obj_dir, src.replace(".cu", ".o"))
     path = os.path.join(CSRC, src)
     if not _stale(obj, [path] + _deps()):
         return obj, ""
-    cmd = [_nvcc(), *NVCC_FLAGS, *_dev_defines(), "-c", path, "-o", obj]
+    cmd = [_nvcc(), *NVCC_FLAGS, *[f"-D{d}=1" for d in defines], "-c", path, "-o", obj]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"nvcc failed on {src}:\n{r.stdout}\n{r.stderr}")
@@ -68,13 +63,23 @@ def _compile(src, verbose):
     return obj, r.stderr if verbose else ""
 
 
-def build(force=False, verbose=False):
+TUNE_LIB = os.path.join(OUT_DIR, "libnngp_b200_tune.so")
+
+
+def build_tune(force=False):
+    """The DEVELOPMENT library tools/tune.py loads explicitly: same sources with NNGP_TUNE (extra kernel shapes selected
+    by NNGP_TUNE_SHAPE).  The product library never contains those knobs."""
+    return build(force=force, lib=TUNE_LIB, obj_dir=os.path.join(OUT_DIR, "obj_tune"), defines=("NNGP_TUNE",))
+
+
+def build(force=False, verbose=False, lib=LIB, obj_dir=OBJ_DIR, defines=()):
+    LIB, OBJ_DIR = lib, obj_dir  # noqa: N806 (shadow the module defaults for a development build)
     os.makedirs(OBJ_DIR, exist_ok=True)
     if force:
         for f in os.listdir(OBJ_DIR):
             os.remove(os.path.join(OBJ_DIR, f))
     with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:
-        results = list(ex.map(lambda s: _compile(s, verbose), SOURCES))
+        results = list(ex.map(lambda s: _compile(s, verbose, OBJ_DIR, defines), SOURCES))
     objs = [o for o, _ in results]
     if verbose:
         for _, log in results:
@@ -89,4 +94,7 @@ def build(force=False, verbose=False):
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))
+    if "--tune" in sys.argv:
+        print(build_tune(force="--force" in sys.argv))
+    else:
+        print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))

@@ -316,6 +316,59 @@ __host__ __device__ constexpr int pair_slot(int t)
     return (j + 1) / G + t;
 }
 
+// FOLD: the folded row assignment.  Lane q of a group owns row s*G + q in even row blocks and row s*G + (G-1-q) in
+// odd ones.  A row needs the columns below it: every column of the blocks before its own (the same for all lanes)
+// plus, inside its own (diagonal) block, q columns in an even block and G-1-q in an odd one -- G-1 per PAIR of
+// blocks, whatever the lane.  So the diagonal blocks of a block pair (s0, s1) cost G-1 evaluation slots instead of
+// 2(G-1): in slot t the lanes with q > t evaluate (row s0*G+q, column s0*G+t) and the others (row s1*G+G-1-q,
+// column s1*G+G-2-t); both destinations are compile-time registers, and each is a don't-care entry (column >= row)
+// for the lanes that did not mean it, so the value is stored to both without a select.  Every lane then evaluates
+// exactly P(P-1)/2 / G pairs: (4,4) 30 instead of 36, (8,4) 62 instead of 76, (8,2) 15, (16,2) 31.
+template <int G, bool FOLD>
+__host__ __device__ constexpr int row_of(int s, int q) { return (FOLD && (s & 1)) ? s * G + (G - 1 - q) : s * G + q; }
+// full-block pairs of the folded layout, column-major: column j < G(R-1) is needed by the row blocks s > j / G
+template <int G, int R>
+__host__ __device__ constexpr int fpair_col(int t)
+{
+    int j = 0;
+    for (; j < G * (R - 1); ++j) {
+        const int cnt = R - 1 - j / G;
+        if (t < cnt) break;
+        t -= cnt;
+    }
+    return j;
+}
+template <int G, int R>
+__host__ __device__ constexpr int fpair_slot(int t)
+{
+    int j = 0;
+    for (; j < G * (R - 1); ++j) {
+        const int cnt = R - 1 - j / G;
+        if (t < cnt) break;
+        t -= cnt;
+    }
+    return j / G + 1 + t;
+}
+// one evaluation slot of the unrolled build: a full-block pair (row block s, column j), or -- FOLD only -- slot tt of
+// the diagonal blocks of the block pair (s, s1)
+struct SlotInfo {
+    bool diag;
+    int s, j;    // full: row block, column.  diag: first block of the pair, its column s*G + tt
+    int s1, j1;  // diag: second block of the pair, its column s1*G + G-2-tt
+    int tt;
+};
+template <int G, int R, bool FOLD>
+__host__ __device__ constexpr int n_slots() { return FOLD ? G * R * (R - 1) / 2 + (R / 2) * (G - 1) : G * R * (R + 1) / 2 - R; }
+template <int G, int R, bool FOLD>
+__host__ __device__ constexpr SlotInfo slot_info(int t)
+{
+    if (!FOLD) return SlotInfo{false, pair_slot<G, R>(t), pair_col<G, R>(t), 0, 0, 0};
+    constexpr int NFULL = G * R * (R - 1) / 2;
+    if (t < NFULL) return SlotInfo{false, fpair_slot<G, R>(t), fpair_col<G, R>(t), 0, 0, 0};
+    const int u = t - NFULL, p = u / (G - 1), tt = u % (G - 1);
+    return SlotInfo{true, 2 * p, 2 * p * G + tt, 2 * p + 1, (2 * p + 1) * G + G - 2 - tt, tt};
+}
+
 // BUILD = 6: the sweep variant of the unrolled build.  A block evaluates a chunk of up to kSweepChunk
 // parameter vectors per location: the pair distances (d^2 and sqrt: 9 of the 17 FP64 instructions a
 // covariance entry costs) are computed once and kept in registers, and for every parameter vector only
@@ -385,11 +438,12 @@ template <> struct Pair2<float> { using type = float2; };
 // of the instructions the 64-bit shuffles (two SHFL plus their register moves each) cost.
 // EMIT: the variant that also writes per-location outputs (accessors, factors(), prediction); compiled
 // separately so the metric's kernel carries none of its code or registers.
-template <typename T, int G, int R, int KERN, bool DIM3, int MINB, int BUILD, int ELIM, bool EMIT>
+template <typename T, int G, int R, int KERN, bool DIM3, int MINB, int BUILD, int ELIM, bool EMIT, bool FOLD>
 __global__ void __launch_bounds__(kThreads, MINB) fused_loglik_kernel(const __grid_constant__ EvalArgs a)
 {
     constexpr int P = G * R;   // rows of the augmented matrix
     constexpr int W = 32 / G;  // locations per warp
+    static_assert(!FOLD || (R % 2 == 0 && ELIM == 1), "the folded layout pairs row blocks");
     using Pt = StagePt<T, DIM3>;
     using WS = WarpSmem<T, G, R, DIM3, BUILD>;
 
@@ -400,8 +454,9 @@ __global__ void __launch_bounds__(kThreads, MINB) fused_loglik_kernel(const __gr
 #endif
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
-    const int q = lane % G;  // row residue owned by this lane
+    const int q = lane % G;  // this lane's position in its group: it owns rows row_of(s, q)
     const int g = lane / G;  // location slot inside the warp
+    auto rowq = [&](int s) { return row_of<G, FOLD>(s, q); };
 
     T *exp_tab = reinterpret_cast<T *>(smem_raw);  // sigma2 * 2^(j/64) (fp64 path only)
     uint2 *pair_lut = reinterpret_cast<uint2 *>(smem_raw + exp_tab_bytes<T, G, BUILD>());
@@ -519,7 +574,7 @@ __global__ void __launch_bounds__(kThreads, MINB) fused_loglik_kernel(const __gr
         const bool live = grp < ngroups && i < a.hi;
 #pragma unroll
         for (int s = 0; s < R; ++s) {
-            const int r = s * G + q;
+            const int r = rowq(s);
             if (live && r < m && r != P - 1) {
                 asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_addr(idxbuf + s * 32)),
                              "l"(a.nbr + i * m + r)
@@ -536,8 +591,8 @@ __global__ void __launch_bounds__(kThreads, MINB) fused_loglik_kernel(const __gr
 #pragma unroll
         for (int s = 0; s < R; ++s) {
             if (nidx[s] >= 0) {
-                const int slot = g * P + s * G + q;
-                const uint32_t dst = smem_addr(recbuf + (s * G + q) * 32);
+                const int slot = g * P + rowq(s);
+                const uint32_t dst = smem_addr(recbuf + rowq(s) * 32);
                 const double4 *src = a.pts + nidx[s];
                 asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
                 asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst + 16u),
@@ -580,7 +635,7 @@ __global__ void __launch_bounds__(kThreads, MINB) fused_loglik_kernel(const __gr
             const double diag0 = SWEEP ? 1.0 : s_diag[0], inv_s2 = SWEEP ? 1.0 : s_diag[1];  // sweep: set per vector below
 #pragma unroll
             for (int s = 0; s < R; ++s) {
-                const int r = s * G + q;
+                const int r = rowq(s);
                 valid[s] = nidx[s] >= 0;
                 double2 v0 = make_double2(0.0, 0.0), v1 = make_double2(0.0, 0.0);
                 double e2 = 0.0;
@@ -611,7 +666,7 @@ __global__ void __launch_bounds__(kThreads, MINB) fused_loglik_kernel(const __gr
 
         // ---- stage 2: covariance build ------------------------------------------------------------
         T A[R][P];
-        [[maybe_unused]] T Dst[SWEEP ? G * R * (R + 1) / 2 - R : 1];  // sweep: the lane's pair distances
+        [[maybe_unused]] T Dst[SWEEP ? n_slots<G, R, FOLD>() : 1];  // sweep: the lane's pair distances
         if constexpr (BUILD == 1) {
         // A rolled loop over this lane's share of the pair list, CB pairs in lock step (independent
         // dependency chains: one chain cannot fill the FP64 pipe -- 8-cycle DFMA latency).  Operands
@@ -650,17 +705,11 @@ __global__ void __launch_bounds__(kThreads, MINB) fused_loglik_kernel(const __gr
             // the lane's rows come from the tile into registers for the elimination
     #pragma unroll
             for (int s = 0; s < R; ++s) {
-                const int r = s * G + q;
+                const int r = rowq(s);
                 const T *row = tile + r * (r - 1) / 2;
     #pragma unroll
                 for (int j = 0; j < P; ++j)
-                    if (j < s * G + G - 1) {
-                        T v = T(0);
-                        if (j < r) v = row[j];
-                        if (j >= s * G) v = (r == j) ? dg[s] : v;  // diagonal block only
-                        A[s][j] = v;
-                    }
-                A[s][s * G + G - 1] = dg[s];  // last column of the diagonal block: lane G-1's diagonal
+                    if (j < s * G + G) A[s][j] = j < r ? row[j] : T(0);  // entries at and right of the diagonal: don't care
             }
         } else {
             // Row-owner build, fully unrolled.  The lane's pairs (row block s, column j) are enumerated
@@ -670,18 +719,30 @@ __global__ void __launch_bounds__(kThreads, MINB) fused_loglik_kernel(const __gr
             // results go straight to the row registers.
             // BUILD selects the unrolled build's batch width: 0 -> 4, 2 -> 6, 3 -> 9, 4 -> 12 pairs in lock step
             constexpr int CB = BUILD == 0 ? 4 : (BUILD == 2 || BUILD == 6) ? 6 : BUILD == 3 ? 9 : 12;
-            constexpr int NP = G * R * (R + 1) / 2 - R;  // sum over s of (s*G + G - 1)
+            constexpr int NP = n_slots<G, R, FOLD>();
 #pragma unroll
             for (int t0 = 0; t0 < NP; t0 += CB) {
                 T d2[CB];
 #pragma unroll
                 for (int b = 0; b < CB; ++b) {
                     const int t = (t0 + b < NP) ? t0 + b : NP - 1;
-                    const int s = pair_slot<G, R>(t), j = pair_col<G, R>(t);
-                    const Pt cj = stage[j];
-                    const T dx = rx[s] - cj.x, dy = ry[s] - cj.y;
+                    const SlotInfo si = slot_info<G, R, FOLD>(t);
+                    T ax, ay, az;
+                    Pt cj;
+                    if (si.diag) {
+                        // lanes q > tt: (row of block s, column j); the others: (row of block s1, column j1)
+                        const bool first = q > si.tt;
+                        ax = first ? rx[si.s] : rx[si.s1];
+                        ay = first ? ry[si.s] : ry[si.s1];
+                        az = first ? rz[si.s] : rz[si.s1];
+                        cj = stage[first ? si.j : si.j1];
+                    } else {
+                        ax = rx[si.s]; ay = ry[si.s]; az = rz[si.s];
+                        cj = stage[si.j];
+                    }
+                    const T dx = ax - cj.x, dy = ay - cj.y;
                     d2[b] = t_fma(dy, dy, t_fma(dx, dx, tiny_seed<T>()));
-                    if constexpr (DIM3) { const T dz = rz[s] - cj.z; d2[b] = t_fma(dz, dz, d2[b]); }
+                    if constexpr (DIM3) { const T dz = az - cj.z; d2[b] = t_fma(dz, dz, d2[b]); }
                 }
                 if constexpr (SWEEP) {
                     // distances only: they serve every parameter vector of the chunk
@@ -695,15 +756,14 @@ __global__ void __launch_bounds__(kThreads, MINB) fused_loglik_kernel(const __gr
 #pragma unroll
                 for (int b = 0; b < CB; ++b) {
                     if (t0 + b < NP) {
-                        const int s = pair_slot<G, R>(t0 + b), j = pair_col<G, R>(t0 + b);
-                        T v = d2[b];
-                        if (j >= s * G) v = (s * G + q == j) ? dg[s] : v;  // diagonal block only
-                        A[s][j] = v;
+                        const SlotInfo si = slot_info<G, R, FOLD>(t0 + b);
+                        A[si.s][si.j] = d2[b];
+                        if (si.diag) A[si.s1][si.j1] = d2[b];  // a don't-care entry for the lanes that did not mean it
                     }
                 }
             }
 #pragma unroll
-            for (int s = 0; s < R; ++s) A[s][s * G + G - 1] = dg[s];
+            for (int s = 0; s < R; ++s) A[s][s * G + G - 1] = T(0);  // never evaluated, never used
         }
         __syncwarp();  // tile and stage[] are rewritten by the next iteration
 
@@ -712,11 +772,11 @@ __global__ void __launch_bounds__(kThreads, MINB) fused_loglik_kernel(const __gr
             const int64_t o = i - a.lo;
 #pragma unroll
             for (int s = 0; s < R; ++s) {
-                const int r = s * G + q;
+                const int r = rowq(s);
 #pragma unroll
                 for (int j = 0; j < P; ++j) {
                     if (j >= (s + 1) * G || j > r) continue;
-                    const double v = valid[s] ? double(A[s][j]) : 0.0;
+                    const double v = valid[s] ? double(j == r ? dg[s] : A[s][j]) : 0.0;  // the diagonal is carried apart
                     if (r == P - 1) {
                         if (j < m && a.cc) a.cc[o * m + j] = v;
                         if (j == P - 1 && a.cs) a.cs[o] = v;
@@ -736,7 +796,7 @@ __global__ void __launch_bounds__(kThreads, MINB) fused_loglik_kernel(const __gr
         volatile double *ab = accbuf + (SWEEP ? kk * 128 : 0);
         if constexpr (SWEEP) {
             constexpr int CBs = 6;
-            constexpr int NP = G * R * (R + 1) / 2 - R;
+            constexpr int NP = n_slots<G, R, FOLD>();
             const T phik = T(sw_prm[kk][0]), dlt = T(sw_prm[kk][1]), is2 = T(sw_prm[kk][2]);
 #pragma unroll
             for (int s = 0; s < R; ++s) {
@@ -752,20 +812,25 @@ __global__ void __launch_bounds__(kThreads, MINB) fused_loglik_kernel(const __gr
 #pragma unroll
                 for (int b = 0; b < CBs; ++b) {
                     if (t0 + b < NP) {
-                        const int s = pair_slot<G, R>(t0 + b), j = pair_col<G, R>(t0 + b);
-                        T v = x[b];
-                        if (j >= s * G) v = (s * G + q == j) ? dg[s] : v;  // diagonal block only
-                        A[s][j] = v;
+                        const SlotInfo si = slot_info<G, R, FOLD>(t0 + b);
+                        A[si.s][si.j] = x[b];
+                        if (si.diag) A[si.s1][si.j1] = x[b];
                     }
                 }
             }
 #pragma unroll
-            for (int s = 0; s < R; ++s) A[s][s * G + G - 1] = dg[s];
+            for (int s = 0; s < R; ++s) A[s][s * G + G - 1] = T(0);
         }
 
         // ---- stage 3: LDL^T elimination with the right-hand side carried along -----------------
+        // The diagonal of each row lives in its own register d[s] (the entries of A at and right of the diagonal are
+        // don't-care values): which column of A holds a row's diagonal depends on the lane, and a register array
+        // cannot be indexed by the lane.
         bool bad = false;
         T Flast = T(1), rlast = T(0);
+        T d[R];
+#pragma unroll
+        for (int s = 0; s < R; ++s) d[s] = dg[s];
         if constexpr (ELIM == 1) {
             using T2 = typename Pair2<T>::type;
 #pragma unroll
@@ -775,8 +840,8 @@ __global__ void __launch_bounds__(kThreads, MINB) fused_loglik_kernel(const __gr
                 // buffers alternate, so one __syncwarp per pivot orders writes against earlier reads
 #pragma unroll
                 for (int s = 0; s < R; ++s)
-                    if (s * G + G - 1 >= k) col[s * G + q] = A[s][k];
-                if (q == k % G) col[P] = w[k / G];
+                    if (s * G + G - 1 >= k) col[rowq(s)] = (s == k / G && rowq(s) == k) ? d[s] : A[s][k];  // the owner of row k: D_k
+                if (rowq(k / G) == k) col[P] = w[k / G];
                 __syncwarp();
                 const T Dk = col[k], wk = col[P];
                 bad |= !(Dk > T(0));
@@ -791,6 +856,7 @@ __global__ void __launch_bounds__(kThreads, MINB) fused_loglik_kernel(const __gr
                         if (s * G + G - 1 > k) {
                             l[s] = A[s][k] * inv;
                             w[s] = t_fma(-l[s], wk, w[s]);
+                            d[s] = t_fma(-l[s], A[s][k], d[s]);
                         }
                     }
 #pragma unroll
@@ -815,7 +881,7 @@ __global__ void __launch_bounds__(kThreads, MINB) fused_loglik_kernel(const __gr
         } else {
 #pragma unroll
         for (int k = 0; k < P; ++k) {
-            const T Dk = grp_bcast<T, G>(A[k / G][k], k % G);
+            const T Dk = grp_bcast<T, G>(d[k / G], k % G);
             const T wk = grp_bcast<T, G>(w[k / G], k % G);
             bad |= !(Dk > T(0));
             if (k == P - 1) {
@@ -829,6 +895,7 @@ __global__ void __launch_bounds__(kThreads, MINB) fused_loglik_kernel(const __gr
                     if (s * G + G - 1 > k) {
                         l[s] = A[s][k] * inv;
                         w[s] = t_fma(-l[s], wk, w[s]);
+                        d[s] = t_fma(-l[s], A[s][k], d[s]);
                     }
                 }
                 // (constant trip counts + guards: nvcc unrolls inner loops before the outer index is
@@ -881,7 +948,7 @@ __global__ void __launch_bounds__(kThreads, MINB) fused_loglik_kernel(const __gr
                 if (g == gg) {
 #pragma unroll
                     for (int s = 0; s < R; ++s) {
-                        const int r = s * G + q;
+                        const int r = rowq(s);
 #pragma unroll
                         for (int kk = 0; kk < P; ++kk)
                             if (kk < (s + 1) * G && kk < r) dump[r * P + kk] = A[s][kk];
@@ -1023,12 +1090,12 @@ __global__ void __launch_bounds__(kThreads, MINB) fused_loglik_kernel(const __gr
 }
 
 // ---- host-side dispatch of one (T, KERN) family -------------------------------------------------
-template <typename T, int G, int R, int KERN, bool DIM3, int MINB, int BUILD, int ELIM>
+template <typename T, int G, int R, int KERN, bool DIM3, int MINB, int BUILD, int ELIM, bool FOLD>
 cudaError_t launch_one(const EvalArgs &a, int K, int grid_x, cudaStream_t stream)
 {
-    auto kern = fused_loglik_kernel<T, G, R, KERN, DIM3, MINB, BUILD, ELIM, false>;
+    auto kern = fused_loglik_kernel<T, G, R, KERN, DIM3, MINB, BUILD, ELIM, false, FOLD>;
     if constexpr (!sweep_build<BUILD>())
-        if (a.emit) kern = fused_loglik_kernel<T, G, R, KERN, DIM3, MINB, BUILD, ELIM, true>;
+        if (a.emit) kern = fused_loglik_kernel<T, G, R, KERN, DIM3, MINB, BUILD, ELIM, true, FOLD>;
     const size_t smem = smem_bytes<T, G, R, DIM3, BUILD>(a.emit != 0);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
@@ -1040,10 +1107,10 @@ cudaError_t launch_one(const EvalArgs &a, int K, int grid_x, cudaStream_t stream
     return cudaGetLastError();
 }
 
-template <typename T, int G, int R, int KERN, bool DIM3, int MINB, int BUILD, int ELIM>
+template <typename T, int G, int R, int KERN, bool DIM3, int MINB, int BUILD, int ELIM, bool FOLD>
 int blocks_per_sm()
 {
-    auto kern = fused_loglik_kernel<T, G, R, KERN, DIM3, MINB, BUILD, ELIM, false>;
+    auto kern = fused_loglik_kernel<T, G, R, KERN, DIM3, MINB, BUILD, ELIM, false, FOLD>;
     int nb = 0;
     const size_t smem = smem_bytes<T, G, R, DIM3, BUILD>(false);
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -1072,26 +1139,41 @@ struct Launcher {
     int K, grid_x;
     cudaStream_t stream;
     bool sweep() const { return K >= 2 && !a.emit; }
-    template <int G, int R, bool DIM3, int MINB, int BUILD, int ELIM = kElim>
-    cudaError_t run() const { return launch_one<T, G, R, KERN, DIM3, MINB, BUILD, ELIM>(a, K, grid_x, stream); }
+    template <int G, int R, bool DIM3, int MINB, int BUILD, int ELIM = kElim, bool FOLD = false>
+    cudaError_t run() const { return launch_one<T, G, R, KERN, DIM3, MINB, BUILD, ELIM, FOLD>(a, K, grid_x, stream); }
 };
 template <typename T, int KERN>
 struct Describer {
     bool sweep() const { return false; }  // grid sizing follows the single-vector kernel (same shape, same registers)
-    template <int G, int R, bool DIM3, int MINB, int BUILD, int ELIM = kElim>
-    ShapeInfo run() const { return ShapeInfo{blocks_per_sm<T, G, R, KERN, DIM3, MINB, BUILD, ELIM>(), 32 / G}; }
+    template <int G, int R, bool DIM3, int MINB, int BUILD, int ELIM = kElim, bool FOLD = false>
+    ShapeInfo run() const { return ShapeInfo{blocks_per_sm<T, G, R, KERN, DIM3, MINB, BUILD, ELIM, FOLD>(), 32 / G}; }
 };
 
 template <typename T, bool DIM3, typename F>
 auto dispatch_shape(int m, const F &f)
 {
     constexpr bool F64 = sizeof(T) == 8;
-#ifdef NNGP_TUNE  // development knobs for the m <= 15, D < 3 shape (results: DESIGN.md 5.3)
-    if (const char *e = getenv("NNGP_TUNE_SHAPE"); e && m > 7 && m <= 15 && !DIM3) {
-        if (!strcmp(e, "shfl")) return f.template run<4, 4, DIM3, 2, 2, 0>();   // shuffle elimination
-        if (!strcmp(e, "4x4r")) return f.template run<4, 4, DIM3, 2, 1>();      // rolled pair-list build
-        if (!strcmp(e, "m3cb4")) return f.template run<4, 4, DIM3, 3, 0>();     // 12 warps/SM, 4-pair batches
-        if (!strcmp(e, "m2cb12")) return f.template run<4, 4, DIM3, 2, 4>();    // 12-pair batches
+#ifdef NNGP_TUNE  // development knobs (results: DESIGN.md 5.3); never compiled into the shipped library
+    if constexpr (F64) {
+        if (const char *e = getenv("NNGP_TUNE_SHAPE"); e && m > 7 && m <= 15 && !f.sweep()) {
+            if (!strcmp(e, "44")) return f.template run<4, 4, DIM3, 2, 2, 1, false>();    // unfolded row owner (round 1)
+            if (!strcmp(e, "44f")) return f.template run<4, 4, DIM3, 2, 2, 1, true>();    // folded, 6-pair batches
+            if (!strcmp(e, "44f3")) return f.template run<4, 4, DIM3, 3, 0, 1, true>();   // folded, 12 warps/SM, 4-pair
+            if (!strcmp(e, "82f2")) return f.template run<8, 2, DIM3, 2, 2, 1, true>();   // 8 lanes x 2 rows, folded
+            if (!strcmp(e, "82f3")) return f.template run<8, 2, DIM3, 3, 2, 1, true>();
+            if (!strcmp(e, "82f4")) return f.template run<8, 2, DIM3, 4, 2, 1, true>();
+            if (!strcmp(e, "82f4b")) return f.template run<8, 2, DIM3, 4, 0, 1, true>();  // 4-pair batches
+            if (!strcmp(e, "82f5")) return f.template run<8, 2, DIM3, 5, 0, 1, true>();
+        }
+        if (const char *e = getenv("NNGP_TUNE_SHAPE"); e && m > 15 && m <= 31 && !f.sweep()) {
+            if (!strcmp(e, "84")) return f.template run<8, 4, DIM3, 2, 0, 1, false>();
+            if (!strcmp(e, "84f")) return f.template run<8, 4, DIM3, 2, 0, 1, true>();
+            if (!strcmp(e, "84r")) return f.template run<8, 4, DIM3, 2, 1, 1, false>();   // rolled pair-list build
+            if (!strcmp(e, "162f2")) return f.template run<16, 2, DIM3, 2, 2, 1, true>();
+            if (!strcmp(e, "162f3")) return f.template run<16, 2, DIM3, 3, 2, 1, true>();
+            if (!strcmp(e, "162f4")) return f.template run<16, 2, DIM3, 4, 0, 1, true>();
+            if (!strcmp(e, "162f3b")) return f.template run<16, 2, DIM3, 3, 0, 1, true>();
+        }
     }
 #endif
     if constexpr (F64) {  // K >= 2: the sweep variant (distances shared by the parameter vectors)
