@@ -324,7 +324,7 @@ __host__ __device__ constexpr int pair_slot(int t)
 // column s1*G+G-2-t); both destinations are compile-time registers, and each is a don't-care entry (column >= row)
 // for the lanes that did not mean it, so the value is stored to both without a select.  Every lane then evaluates
 // exactly P(P-1)/2 / G pairs: (4,4) 30 instead of 36, (8,4) 62 instead of 76, (8,2) 15, (16,2) 31.
-template <int G, bool FOLD>
+template <int G, int FOLD>
 __host__ __device__ constexpr int row_of(int s, int q) { return (FOLD && (s & 1)) ? s * G + (G - 1 - q) : s * G + q; }
 // full-block pairs of the folded layout, column-major: column j < G(R-1) is needed by the row blocks s > j / G
 template <int G, int R>
@@ -357,12 +357,28 @@ struct SlotInfo {
     int s1, j1;  // diag: second block of the pair, its column s1*G + G-2-tt
     int tt;
 };
-template <int G, int R, bool FOLD>
+template <int G, int R, int FOLD>
 __host__ __device__ constexpr int n_slots() { return FOLD ? G * R * (R - 1) / 2 + (R / 2) * (G - 1) : G * R * (R + 1) / 2 - R; }
-template <int G, int R, bool FOLD>
+// Slot order of the folded layout.  FOLD = 1, column-major over the row blocks: consecutive slots share a column, whose
+// staged coordinates are then loaded once for up to R-1 slots.  FOLD = 2, row-block-major: block after block, the
+// diagonal slots of a block pair right after its second block -- the scaled coordinates of a row block are dead once
+// its slots are done, while the matrix registers fill up, which lowers the peak register need; every slot loads its
+// own column (cheap for 16-byte 2-D points, not for 32-byte 3-D ones).
+template <int G, int R, int FOLD>
 __host__ __device__ constexpr SlotInfo slot_info(int t)
 {
     if (!FOLD) return SlotInfo{false, pair_slot<G, R>(t), pair_col<G, R>(t), 0, 0, 0};
+    if (FOLD == 2) {
+        for (int s = 1; s < R; ++s) {
+            if (t < s * G) return SlotInfo{false, s, t, 0, 0, 0};
+            t -= s * G;
+            if (s & 1) {
+                if (t < G - 1) return SlotInfo{true, s - 1, (s - 1) * G + t, s, s * G + G - 2 - t, t};
+                t -= G - 1;
+            }
+        }
+        return SlotInfo{false, R - 1, 0, 0, 0, 0};  // not reached for t < n_slots
+    }
     constexpr int NFULL = G * R * (R - 1) / 2;
     if (t < NFULL) return SlotInfo{false, fpair_slot<G, R>(t), fpair_col<G, R>(t), 0, 0, 0};
     const int u = t - NFULL, p = u / (G - 1), tt = u % (G - 1);
@@ -438,7 +454,7 @@ template <> struct Pair2<float> { using type = float2; };
 // of the instructions the 64-bit shuffles (two SHFL plus their register moves each) cost.
 // EMIT: the variant that also writes per-location outputs (accessors, factors(), prediction); compiled
 // separately so the metric's kernel carries none of its code or registers.
-template <typename T, int G, int R, int KERN, bool DIM3, int MINB, int BUILD, int ELIM, bool EMIT, bool FOLD>
+template <typename T, int G, int R, int KERN, bool DIM3, int MINB, int BUILD, int ELIM, bool EMIT, int FOLD>
 __global__ void __launch_bounds__(kThreads, MINB) fused_loglik_kernel(const __grid_constant__ EvalArgs a)
 {
     constexpr int P = G * R;   // rows of the augmented matrix
@@ -666,6 +682,18 @@ __global__ void __launch_bounds__(kThreads, MINB) fused_loglik_kernel(const __gr
 
         // ---- stage 2: covariance build ------------------------------------------------------------
         T A[R][P];
+        // The diagonal entry of the lane's row in block s sits in column s*G + q (even blocks) or s*G + G-1-q (odd blocks
+        // of the folded layout): a register array cannot be indexed by the lane, so it is placed by selects over the
+        // block's columns.  The block's last column is a diagonal only for the lane whose row it is and a don't-care
+        // entry for every other lane: no select there.
+        auto set_diag = [&](T (&M)[R][P], const T (&dgv)[R]) {
+#pragma unroll
+            for (int s = 0; s < R; ++s) {
+#pragma unroll
+                for (int c = 0; c < G - 1; ++c) M[s][s * G + c] = (rowq(s) == s * G + c) ? dgv[s] : M[s][s * G + c];
+                M[s][s * G + G - 1] = dgv[s];
+            }
+        };
         [[maybe_unused]] T Dst[SWEEP ? n_slots<G, R, FOLD>() : 1];  // sweep: the lane's pair distances
         if constexpr (BUILD == 1) {
         // A rolled loop over this lane's share of the pair list, CB pairs in lock step (independent
@@ -709,8 +737,9 @@ __global__ void __launch_bounds__(kThreads, MINB) fused_loglik_kernel(const __gr
                 const T *row = tile + r * (r - 1) / 2;
     #pragma unroll
                 for (int j = 0; j < P; ++j)
-                    if (j < s * G + G) A[s][j] = j < r ? row[j] : T(0);  // entries at and right of the diagonal: don't care
+                    if (j < s * G + G) A[s][j] = j < r ? row[j] : T(0);  // entries right of the diagonal: don't care
             }
+            set_diag(A, dg);
         } else {
             // Row-owner build, fully unrolled.  The lane's pairs (row block s, column j) are enumerated
             // column-major at compile time and evaluated CB at a time in lock step -- always CB
@@ -762,8 +791,7 @@ __global__ void __launch_bounds__(kThreads, MINB) fused_loglik_kernel(const __gr
                     }
                 }
             }
-#pragma unroll
-            for (int s = 0; s < R; ++s) A[s][s * G + G - 1] = T(0);  // never evaluated, never used
+            set_diag(A, dg);
         }
         __syncwarp();  // tile and stage[] are rewritten by the next iteration
 
@@ -776,7 +804,7 @@ __global__ void __launch_bounds__(kThreads, MINB) fused_loglik_kernel(const __gr
 #pragma unroll
                 for (int j = 0; j < P; ++j) {
                     if (j >= (s + 1) * G || j > r) continue;
-                    const double v = valid[s] ? double(j == r ? dg[s] : A[s][j]) : 0.0;  // the diagonal is carried apart
+                    const double v = valid[s] ? double(A[s][j]) : 0.0;
                     if (r == P - 1) {
                         if (j < m && a.cc) a.cc[o * m + j] = v;
                         if (j == P - 1 && a.cs) a.cs[o] = v;
@@ -818,19 +846,12 @@ __global__ void __launch_bounds__(kThreads, MINB) fused_loglik_kernel(const __gr
                     }
                 }
             }
-#pragma unroll
-            for (int s = 0; s < R; ++s) A[s][s * G + G - 1] = T(0);
+            set_diag(A, dg);
         }
 
         // ---- stage 3: LDL^T elimination with the right-hand side carried along -----------------
-        // The diagonal of each row lives in its own register d[s] (the entries of A at and right of the diagonal are
-        // don't-care values): which column of A holds a row's diagonal depends on the lane, and a register array
-        // cannot be indexed by the lane.
         bool bad = false;
         T Flast = T(1), rlast = T(0);
-        T d[R];
-#pragma unroll
-        for (int s = 0; s < R; ++s) d[s] = dg[s];
         if constexpr (ELIM == 1) {
             using T2 = typename Pair2<T>::type;
 #pragma unroll
@@ -840,7 +861,7 @@ __global__ void __launch_bounds__(kThreads, MINB) fused_loglik_kernel(const __gr
                 // buffers alternate, so one __syncwarp per pivot orders writes against earlier reads
 #pragma unroll
                 for (int s = 0; s < R; ++s)
-                    if (s * G + G - 1 >= k) col[rowq(s)] = (s == k / G && rowq(s) == k) ? d[s] : A[s][k];  // the owner of row k: D_k
+                    if (s * G + G - 1 >= k) col[rowq(s)] = A[s][k];
                 if (rowq(k / G) == k) col[P] = w[k / G];
                 __syncwarp();
                 const T Dk = col[k], wk = col[P];
@@ -856,7 +877,6 @@ __global__ void __launch_bounds__(kThreads, MINB) fused_loglik_kernel(const __gr
                         if (s * G + G - 1 > k) {
                             l[s] = A[s][k] * inv;
                             w[s] = t_fma(-l[s], wk, w[s]);
-                            d[s] = t_fma(-l[s], A[s][k], d[s]);
                         }
                     }
 #pragma unroll
@@ -881,7 +901,7 @@ __global__ void __launch_bounds__(kThreads, MINB) fused_loglik_kernel(const __gr
         } else {
 #pragma unroll
         for (int k = 0; k < P; ++k) {
-            const T Dk = grp_bcast<T, G>(d[k / G], k % G);
+            const T Dk = grp_bcast<T, G>(A[k / G][k], k % G);
             const T wk = grp_bcast<T, G>(w[k / G], k % G);
             bad |= !(Dk > T(0));
             if (k == P - 1) {
@@ -895,7 +915,6 @@ __global__ void __launch_bounds__(kThreads, MINB) fused_loglik_kernel(const __gr
                     if (s * G + G - 1 > k) {
                         l[s] = A[s][k] * inv;
                         w[s] = t_fma(-l[s], wk, w[s]);
-                        d[s] = t_fma(-l[s], A[s][k], d[s]);
                     }
                 }
                 // (constant trip counts + guards: nvcc unrolls inner loops before the outer index is
@@ -1090,7 +1109,7 @@ __global__ void __launch_bounds__(kThreads, MINB) fused_loglik_kernel(const __gr
 }
 
 // ---- host-side dispatch of one (T, KERN) family -------------------------------------------------
-template <typename T, int G, int R, int KERN, bool DIM3, int MINB, int BUILD, int ELIM, bool FOLD>
+template <typename T, int G, int R, int KERN, bool DIM3, int MINB, int BUILD, int ELIM, int FOLD>
 cudaError_t launch_one(const EvalArgs &a, int K, int grid_x, cudaStream_t stream)
 {
     auto kern = fused_loglik_kernel<T, G, R, KERN, DIM3, MINB, BUILD, ELIM, false, FOLD>;
@@ -1107,7 +1126,7 @@ cudaError_t launch_one(const EvalArgs &a, int K, int grid_x, cudaStream_t stream
     return cudaGetLastError();
 }
 
-template <typename T, int G, int R, int KERN, bool DIM3, int MINB, int BUILD, int ELIM, bool FOLD>
+template <typename T, int G, int R, int KERN, bool DIM3, int MINB, int BUILD, int ELIM, int FOLD>
 int blocks_per_sm()
 {
     auto kern = fused_loglik_kernel<T, G, R, KERN, DIM3, MINB, BUILD, ELIM, false, FOLD>;
@@ -1119,12 +1138,16 @@ int blocks_per_sm()
 }
 
 // ---- shape table: (G lanes per location, R rows per lane) -> P = G*R >= m + 1 rows --------------------
-//   m <=  7 : (4, 2) unrolled row-owner build
-//   m <= 15 : (4, 4) unrolled row-owner build, fp64: 6-pair batches, 255 registers, 8 warps/SM (in-thread
-//             parallelism hides the FP64 latency better than a third block of warps did: 0.433 vs 0.452 ms)
-//   m <= 31 : (8, 4); fp64 3-D: unrolled row-owner build (5.96 vs 6.26 ms per 2e6 locations at m = 30), otherwise the
-//             rolled pair-list build (2-D: 5.12 vs 5.22 ms -- the unrolled form spills more there)
-//   m == 32 : (16, 3) rolled pair-list build
+// fp64 (the folded layout, every lane evaluating exactly P(P-1)/2G pairs):
+//   m <=  7 : (4, 2) folded, 4-pair batches
+//   m <= 15 : (4, 4) folded, 6-pair batches, 255 registers, 8 warps/SM (in-thread parallelism hides the FP64 latency
+//             better than a third block of warps: 0.432 ms at cfg3 against 0.514; unfolded 0.440; (8, 2) folded at
+//             8 / 12 / 16 warps per SM 0.577 / 0.588 / 0.614 -- half the rows per lane means half the locations per
+//             warp, and the per-iteration bookkeeping does not shrink with them)
+//   m <= 31 : (16, 2) folded, 6-pair batches: 5.37 ms per 2e6 locations at m = 30 in 3-D against 6.02 for the unfolded
+//             (8, 4) it replaces (folded (8, 4): 5.74); 2-D 4.78 against 5.14 for the rolled pair-list build
+//   m == 32 : (16, 3) rolled pair-list build (three row blocks do not pair)
+// fp32: (4, 2) / (4, 4) row owner, (8, 4) / (16, 3) rolled pair-list build, 16 warps/SM.
 // MINB = resident blocks per SM the kernel is compiled for (the register cap).
 struct ShapeInfo {
     int blocks_per_sm;
@@ -1139,13 +1162,13 @@ struct Launcher {
     int K, grid_x;
     cudaStream_t stream;
     bool sweep() const { return K >= 2 && !a.emit; }
-    template <int G, int R, bool DIM3, int MINB, int BUILD, int ELIM = kElim, bool FOLD = false>
+    template <int G, int R, bool DIM3, int MINB, int BUILD, int ELIM = kElim, int FOLD = 0>
     cudaError_t run() const { return launch_one<T, G, R, KERN, DIM3, MINB, BUILD, ELIM, FOLD>(a, K, grid_x, stream); }
 };
 template <typename T, int KERN>
 struct Describer {
     bool sweep() const { return false; }  // grid sizing follows the single-vector kernel (same shape, same registers)
-    template <int G, int R, bool DIM3, int MINB, int BUILD, int ELIM = kElim, bool FOLD = false>
+    template <int G, int R, bool DIM3, int MINB, int BUILD, int ELIM = kElim, int FOLD = 0>
     ShapeInfo run() const { return ShapeInfo{blocks_per_sm<T, G, R, KERN, DIM3, MINB, BUILD, ELIM, FOLD>(), 32 / G}; }
 };
 
@@ -1156,34 +1179,41 @@ auto dispatch_shape(int m, const F &f)
 #ifdef NNGP_TUNE  // development knobs (results: DESIGN.md 5.3); never compiled into the shipped library
     if constexpr (F64) {
         if (const char *e = getenv("NNGP_TUNE_SHAPE"); e && m > 7 && m <= 15 && !f.sweep()) {
-            if (!strcmp(e, "44")) return f.template run<4, 4, DIM3, 2, 2, 1, false>();    // unfolded row owner (round 1)
-            if (!strcmp(e, "44f")) return f.template run<4, 4, DIM3, 2, 2, 1, true>();    // folded, 6-pair batches
-            if (!strcmp(e, "44f3")) return f.template run<4, 4, DIM3, 3, 0, 1, true>();   // folded, 12 warps/SM, 4-pair
-            if (!strcmp(e, "82f2")) return f.template run<8, 2, DIM3, 2, 2, 1, true>();   // 8 lanes x 2 rows, folded
-            if (!strcmp(e, "82f3")) return f.template run<8, 2, DIM3, 3, 2, 1, true>();
-            if (!strcmp(e, "82f4")) return f.template run<8, 2, DIM3, 4, 2, 1, true>();
-            if (!strcmp(e, "82f4b")) return f.template run<8, 2, DIM3, 4, 0, 1, true>();  // 4-pair batches
-            if (!strcmp(e, "82f5")) return f.template run<8, 2, DIM3, 5, 0, 1, true>();
+            if (!strcmp(e, "44")) return f.template run<4, 4, DIM3, 2, 2, 1, 0>();    // unfolded row owner (round 1)
+            if (!strcmp(e, "44f")) return f.template run<4, 4, DIM3, 2, 2, 1, 1>();   // folded, 6-pair batches
+            if (!strcmp(e, "44g")) return f.template run<4, 4, DIM3, 2, 2, 1, 2>();   // folded, row-block-major slots
+            if (!strcmp(e, "44f4")) return f.template run<4, 4, DIM3, 2, 0, 1, 1>();  // folded, 4-pair batches
+            if (!strcmp(e, "82f3")) return f.template run<8, 2, DIM3, 3, 2, 1, 1>();  // 8 lanes x 2 rows, 12 warps/SM
         }
         if (const char *e = getenv("NNGP_TUNE_SHAPE"); e && m > 15 && m <= 31 && !f.sweep()) {
-            if (!strcmp(e, "84")) return f.template run<8, 4, DIM3, 2, 0, 1, false>();
-            if (!strcmp(e, "84f")) return f.template run<8, 4, DIM3, 2, 0, 1, true>();
-            if (!strcmp(e, "84r")) return f.template run<8, 4, DIM3, 2, 1, 1, false>();   // rolled pair-list build
-            if (!strcmp(e, "162f2")) return f.template run<16, 2, DIM3, 2, 2, 1, true>();
-            if (!strcmp(e, "162f3")) return f.template run<16, 2, DIM3, 3, 2, 1, true>();
-            if (!strcmp(e, "162f4")) return f.template run<16, 2, DIM3, 4, 0, 1, true>();
-            if (!strcmp(e, "162f3b")) return f.template run<16, 2, DIM3, 3, 0, 1, true>();
+            if (!strcmp(e, "84")) return f.template run<8, 4, DIM3, 2, 0, 1, 0>();
+            if (!strcmp(e, "84f")) return f.template run<8, 4, DIM3, 2, 0, 1, 1>();
+            if (!strcmp(e, "84g")) return f.template run<8, 4, DIM3, 2, 0, 1, 2>();
+            if (!strcmp(e, "84f6")) return f.template run<8, 4, DIM3, 2, 2, 1, 1>();  // 6-pair batches
+            if (!strcmp(e, "84r")) return f.template run<8, 4, DIM3, 2, 1, 1, 0>();   // rolled pair-list build
+            if (!strcmp(e, "162f")) return f.template run<16, 2, DIM3, 2, 2, 1, 1>();
+            if (!strcmp(e, "162g")) return f.template run<16, 2, DIM3, 2, 2, 1, 2>();
+            if (!strcmp(e, "162f4")) return f.template run<16, 2, DIM3, 2, 0, 1, 1>();
+            if (!strcmp(e, "162g4")) return f.template run<16, 2, DIM3, 2, 0, 1, 2>();
+            if (!strcmp(e, "162g3")) return f.template run<16, 2, DIM3, 3, 0, 1, 2>();
         }
     }
 #endif
     if constexpr (F64) {  // K >= 2: the sweep variant (distances shared by the parameter vectors)
-        if (m <= 7 && f.sweep()) return f.template run<4, 2, DIM3, 4, 6>();
-        if (m <= 15 && f.sweep()) return f.template run<4, 4, DIM3, 2, 6>();
+        if (m <= 7 && f.sweep()) return f.template run<4, 2, DIM3, 4, 6, kElim, 1>();
+        if (m <= 15 && f.sweep()) return f.template run<4, 4, DIM3, 2, 6, kElim, 1>();
+        if (m <= 31 && f.sweep()) return f.template run<16, 2, DIM3, 2, 6, kElim, 1>();
+        // fp64 single vector: the folded layouts (measured, tools/tune.py: DESIGN.md 5.3)
+        if (m <= 7) return f.template run<4, 2, DIM3, 4, 0, kElim, 1>();
+        if (m <= 15) return f.template run<4, 4, DIM3, 2, 2, kElim, 1>();
+        if (m <= 31) return f.template run<16, 2, DIM3, 2, 2, kElim, 1>();
+        return f.template run<16, 3, DIM3, 2, 1>();
+    } else {
+        if (m <= 7) return f.template run<4, 2, DIM3, 4, 0>();
+        if (m <= 15) return f.template run<4, 4, DIM3, 4, 0>();
+        if (m <= 31) return f.template run<8, 4, DIM3, 4, 1>();
+        return f.template run<16, 3, DIM3, 4, 1>();
     }
-    if (m <= 7) return f.template run<4, 2, DIM3, 4, 0>();
-    if (m <= 15) return f.template run<4, 4, DIM3, (F64 ? 2 : 4), (F64 ? 2 : 0)>();
-    if (m <= 31) return f.template run<8, 4, DIM3, (F64 ? 2 : 4), (F64 && DIM3 ? 0 : 1)>();
-    return f.template run<16, 3, DIM3, (F64 ? 2 : 4), 1>();
 }
 
 template <typename T, int KERN>

@@ -263,9 +263,11 @@ def test_batched_params_and_determinism():
     s, y = synthetic(5000, 2, 8)
     nbr = orc.c_knn_ordered(s, 15, threads=4)
     eps2 = np.linspace(0.0, 0.05, 5000)
-    for kid, m_use in ((1, 15), (0, 9), (2, 12), (1, 5)):
+    nbr30 = orc.c_knn_ordered(s, 30, threads=4)
+    for kid, m_use in ((1, 15), (0, 9), (2, 12), (1, 5), (1, 30), (0, 17)):
         e = engine(s, y, eps2)
-        e.set_neighbors(np.ascontiguousarray(np.where(np.arange(15)[None, :] < m_use, nbr, -1)[:, :m_use]))
+        src = nbr if m_use <= 15 else nbr30
+        e.set_neighbors(np.ascontiguousarray(np.where(np.arange(src.shape[1])[None, :] < m_use, src, -1)[:, :m_use]))
         tab = e.get_neighbors()
         rng = np.random.default_rng(kid)
         K = 11
