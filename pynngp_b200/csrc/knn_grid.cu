@@ -28,13 +28,12 @@
 #include <stdint.h>
 
 #include <algorithm>
+#include <type_traits>
 
 #include "nngp_common.cuh"
 #include "peer_exchange.cuh"
 
 namespace nngp_grid {
-
-constexpr int TQ = 128;  // queries (threads) per block
 
 struct GridSpec {
     double lo[3];     // bounding box minimum
@@ -153,52 +152,53 @@ __global__ void scatter_kernel(const double4 *__restrict__ pts, int N, int ncand
     }
 }
 
-// the m best (d2, j) of one query: a column of shared memory per thread, sorted ascending
-struct TopM {
-    double *keys;  // [m][TQ]
-    int32_t *ids;
-    int m, cnt;
-    double worst;      // keys[m-1] once full, +inf before
-    int32_t worst_id;  // ids[m-1] once full
+// ---- the query kernel: SW lanes per query, warp-level top-m selection ----------------------------------------
+// A query is searched by a sub-warp of SW lanes (SW = 8 / 16 / 32 >= m; a warp carries 32 / SW queries, neighbours
+// in the cell-sorted query list, so its sub-warps walk the same cells).  The m best (d2, j) found so far live in
+// REGISTERS, one entry per lane: lane k of the sub-warp holds the k-th best in the total order (d2, j), empty
+// entries hold (+inf, INT_MAX) and sort last.  A span of records (one row of cells) is read SW at a time --
+// consecutive lanes, consecutive 32-byte records -- every lane evaluates the scikit-learn squared distance of its
+// candidate, and a ballot collects the candidates that beat the sub-warp's current m-th best.  Each survivor is
+// then inserted by the whole sub-warp: its (d2, j) is broadcast from the lane that holds it, every list lane
+// compares its own entry against it, the population count of that ballot is the insertion position, and the tail
+// of the list moves up one lane with __shfl_up_sync (the old m-th best falls off the end).  Nothing is kept in
+// shared memory and no lane loops over the list.  d2 >= +0 always, so (d2, j) is compared on the bit patterns --
+// unsigned 64-bit order equals numeric order for non-negative doubles -- which keeps the FP64 pipe for distances.
+// The threshold the ballot uses is refreshed once per SW candidates, not per insertion: a stale threshold only
+// lets a few candidates through that land beyond position m - 1, where they are dropped.
+constexpr int QTHREADS = 256;  // threads per block of the query kernel
+constexpr int32_t kNoId = 0x7fffffff;
 
-    __device__ __forceinline__ bool accepts(double d2, int32_t j) const
-    {
-        return d2 < worst || (d2 == worst && j < worst_id);
-    }
-    __device__ __forceinline__ void insert(double d2, int32_t j)
-    {
-        int pos = cnt < m ? cnt : m - 1;
-        while (pos > 0) {
-            const double kp = keys[(pos - 1) * TQ];
-            const int32_t ip = ids[(pos - 1) * TQ];
-            if (!(d2 < kp || (d2 == kp && j < ip))) break;
-            keys[pos * TQ] = kp;
-            ids[pos * TQ] = ip;
-            --pos;
-        }
-        keys[pos * TQ] = d2;
-        ids[pos * TQ] = j;
-        if (cnt < m) ++cnt;
-        if (cnt == m) { worst = keys[(m - 1) * TQ]; worst_id = ids[(m - 1) * TQ]; }
-    }
+struct Cand {
+    unsigned long long key;  // bit pattern of d2 (>= +0)
+    int32_t id;
 };
+__device__ __forceinline__ bool cand_less(unsigned long long ka, int32_t ia, unsigned long long kb, int32_t ib)
+{
+    return ka < kb || (ka == kb && ia < ib);
+}
 
 // ORDERED: candidates are the predecessors j < i.  !ORDERED: every grid point, the query included
 // (the plain k-NN behind the reference's `ws`, nngp.py:45-47).
-template <bool DIM3, bool ORDERED>
-__global__ void __launch_bounds__(TQ) knn_grid_query_kernel(const double4 *__restrict__ pts,
-                                                            const double4 *__restrict__ sorted,
-                                                            const int *__restrict__ starts,
-                                                            const int *__restrict__ cell_of,
-                                                            const int *__restrict__ qlist, int nq, GridSpec gs, int m,
-                                                            int cand_cap, int32_t *__restrict__ out)
+template <bool DIM3, bool ORDERED, int SW>
+__global__ void __launch_bounds__(QTHREADS) knn_grid_query_kernel(const double4 *__restrict__ pts,
+                                                                  const double4 *__restrict__ sorted,
+                                                                  const int *__restrict__ starts,
+                                                                  const int *__restrict__ cell_of,
+                                                                  const int *__restrict__ qlist, int nq, GridSpec gs, int m,
+                                                                  int cand_cap, int32_t *__restrict__ out)
 {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    double *keys_all = reinterpret_cast<double *>(smem_raw);
-    int32_t *ids_all = reinterpret_cast<int32_t *>(keys_all + size_t(m) * TQ);
-    const int t = blockIdx.x * TQ + threadIdx.x;
-    if (t >= nq) return;
-    const int i = qlist[t];
+    constexpr unsigned FULL = 0xffffffffu;
+    constexpr unsigned SUBMASK = 0xffffffffu >> (32 - SW);
+    constexpr unsigned long long kInf = 0x7ff0000000000000ull;
+    const int lane = threadIdx.x & 31;
+    const int sl = lane % SW;             // lane inside the sub-warp = list position it holds
+    const int sshift = lane - sl;         // first lane of the sub-warp
+    const int t = (blockIdx.x * (QTHREADS / 32) + (threadIdx.x >> 5)) * (32 / SW) + lane / SW;
+    // a sub-warp without a query walks along with an empty box (whole warps leave)
+    if ((blockIdx.x * (QTHREADS / 32) + (threadIdx.x >> 5)) * (32 / SW) >= nq) return;
+    const bool has_q = t < nq;
+    const int i = has_q ? qlist[t] : 0;
     const double4 q = pts[i];
     const double qx = q.x, qy = q.y, qz = q.z;
     const int Gx = gs.G[0], Gy = gs.G[1], Gz = gs.G[2];
@@ -208,64 +208,100 @@ __global__ void __launch_bounds__(TQ) knn_grid_query_kernel(const double4 *__res
     c /= Gx;
     const int cy = c % Gy, cz = c / Gy;
 
-    TopM top;
-    top.keys = keys_all + threadIdx.x;
-    top.ids = ids_all + threadIdx.x;
-    top.m = m;
-    top.cnt = 0;
-    top.worst = INFINITY;
-    top.worst_id = 0x7fffffff;
+    unsigned long long key = kInf;  // this lane's list entry
+    int32_t id = kNoId;
+    unsigned long long worst = kInf;  // the sub-warp's m-th best (the acceptance threshold), refreshed per batch
+    int32_t worst_id = kNoId;
 
     const double2 *rec = reinterpret_cast<const double2 *>(sorted);
+    // scans records [s, e) of the sub-warp's query (s >= e: nothing); sub-warps of a warp run in lock step
     auto scan_span = [&](int s, int e) {
-        for (int k = s; k < e; ++k) {
-            const double2 a = __ldg(rec + 2 * k), b = __ldg(rec + 2 * k + 1);
-            const int32_t j = __double2loint(b.y);
-            // scikit-learn's order of operations, no contraction (bit-exact with knn_ordered.cu)
-            const double dx = qx - a.x, dy = qy - a.y;
-            double d = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
-            if (DIM3) {
-                const double dz = qz - b.x;
-                d = __dadd_rn(d, __dmul_rn(dz, dz));
+        for (int base = s; __any_sync(FULL, base < e); base += SW) {
+            const int k = base + sl;
+            Cand cd{kInf, kNoId};
+            bool pass = false;
+            if (k < e) {
+                const double2 a = __ldg(rec + 2 * k), b = __ldg(rec + 2 * k + 1);
+                cd.id = __double2loint(b.y);
+                // scikit-learn's order of operations, no contraction (bit-exact with knn_ordered.cu)
+                const double dx = qx - a.x, dy = qy - a.y;
+                double d = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
+                if (DIM3) {
+                    const double dz = qz - b.x;
+                    d = __dadd_rn(d, __dmul_rn(dz, dz));
+                }
+                cd.key = (unsigned long long)__double_as_longlong(d);
+                pass = (!ORDERED || cd.id < jlim) && cand_less(cd.key, cd.id, worst, worst_id);
             }
-            if ((!ORDERED || j < jlim) && top.accepts(d, j)) top.insert(d, j);
+            unsigned todo = (__ballot_sync(FULL, pass) >> sshift) & SUBMASK;  // this sub-warp's survivors
+            while (__any_sync(FULL, todo != 0)) {
+                const bool act = todo != 0;
+                const int src = act ? __ffs(todo) - 1 : 0;
+                const unsigned long long ck = __shfl_sync(FULL, cd.key, src, SW);
+                const int32_t cj = __shfl_sync(FULL, cd.id, src, SW);
+                // list entries that sort before the candidate form a prefix: its length is the position
+                const bool before = sl < m && cand_less(key, id, ck, cj);
+                const int pos = __popc((__ballot_sync(FULL, before) >> sshift) & SUBMASK);
+                const unsigned long long kup = __shfl_up_sync(FULL, key, 1, SW);
+                const int32_t iup = __shfl_up_sync(FULL, id, 1, SW);
+                if (act) {
+                    if (sl == pos) { key = ck; id = cj; }
+                    else if (sl > pos) { key = kup; id = iup; }
+                }
+                todo &= todo - 1;
+            }
+            worst = __shfl_sync(FULL, key, m - 1, SW);
+            worst_id = __shfl_sync(FULL, id, m - 1, SW);
         }
     };
 
-    for (int r = 1;; ++r) {
+    bool done = !has_q;
+    for (int r = 1; !__all_sync(FULL, done); ++r) {
         const int x0 = max(cx - r, 0), x1 = min(cx + r, Gx - 1);
         const int y0 = max(cy - r, 0), y1 = min(cy + r, Gy - 1);
         const int z0 = max(cz - r, 0), z1 = min(cz + r, Gz - 1);
-        for (int zz = z0; zz <= z1; ++zz) {
-            const bool zshell = (zz - cz == r) || (cz - zz == r);
-            for (int yy = y0; yy <= y1; ++yy) {
+        // lock step over the (2r+1)^2 rows of cells of the box: rows outside a sub-warp's own box are empty spans
+        for (int dz = DIM3 ? -r : 0; dz <= (DIM3 ? r : 0); ++dz) {
+            const int zz = cz + dz;
+            const bool zin = !done && zz >= z0 && zz <= z1;
+            const bool zshell = dz == r || dz == -r;
+            for (int dy = -r; dy <= r; ++dy) {
+                const int yy = cy + dy;
+                const bool in = zin && yy >= y0 && yy <= y1;
                 const int rowbase = (zz * Gy + yy) * Gx;
-                if (r == 1 || zshell || yy - cy == r || cy - yy == r) {
+                if (r == 1 || (DIM3 && zshell) || dy == r || dy == -r) {
                     // a row of cells new to this ring: one contiguous span of records
-                    scan_span(starts[rowbase + x0], starts[rowbase + x1 + 1]);
+                    int s = 0, e = 0;
+                    if (in) { s = starts[rowbase + x0]; e = starts[rowbase + x1 + 1]; }
+                    scan_span(s, e);
                 } else {
-                    if (cx - r >= 0) scan_span(starts[rowbase + cx - r], starts[rowbase + cx - r + 1]);
-                    if (cx + r <= Gx - 1) scan_span(starts[rowbase + cx + r], starts[rowbase + cx + r + 1]);
+                    int s = 0, e = 0;
+                    if (in && cx - r >= 0) { s = starts[rowbase + cx - r]; e = starts[rowbase + cx - r + 1]; }
+                    scan_span(s, e);
+                    s = 0; e = 0;
+                    if (in && cx + r <= Gx - 1) { s = starts[rowbase + cx + r]; e = starts[rowbase + cx + r + 1]; }
+                    scan_span(s, e);
                 }
             }
         }
-        if (x0 == 0 && x1 == Gx - 1 && y0 == 0 && y1 == Gy - 1 && z0 == 0 && z1 == Gz - 1) break;
-        if (top.cnt == m) {
-            // distance from the query to the nearest face of the visited box that has cells behind it
-            double bound = INFINITY;
-            if (cx - r > 0) bound = fmin(bound, qx - (gs.lo[0] + double(cx - r) * gs.h[0]));
-            if (cx + r < Gx - 1) bound = fmin(bound, (gs.lo[0] + double(cx + r + 1) * gs.h[0]) - qx);
-            if (cy - r > 0) bound = fmin(bound, qy - (gs.lo[1] + double(cy - r) * gs.h[1]));
-            if (cy + r < Gy - 1) bound = fmin(bound, (gs.lo[1] + double(cy + r + 1) * gs.h[1]) - qy);
-            if (cz - r > 0) bound = fmin(bound, qz - (gs.lo[2] + double(cz - r) * gs.h[2]));
-            if (cz + r < Gz - 1) bound = fmin(bound, (gs.lo[2] + double(cz + r + 1) * gs.h[2]) - qz);
-            const double bs = bound * (1.0 - 1e-9) - gs.slack;
-            if (bs > 0.0 && top.worst < bs * bs) break;
+        if (!done) {
+            if (x0 == 0 && x1 == Gx - 1 && y0 == 0 && y1 == Gy - 1 && z0 == 0 && z1 == Gz - 1) done = true;
+            else if (worst_id != kNoId) {  // the list is full
+                // distance from the query to the nearest face of the visited box that has cells behind it
+                double bound = INFINITY;
+                if (cx - r > 0) bound = fmin(bound, qx - (gs.lo[0] + double(cx - r) * gs.h[0]));
+                if (cx + r < Gx - 1) bound = fmin(bound, (gs.lo[0] + double(cx + r + 1) * gs.h[0]) - qx);
+                if (cy - r > 0) bound = fmin(bound, qy - (gs.lo[1] + double(cy - r) * gs.h[1]));
+                if (cy + r < Gy - 1) bound = fmin(bound, (gs.lo[1] + double(cy + r + 1) * gs.h[1]) - qy);
+                if (cz - r > 0) bound = fmin(bound, qz - (gs.lo[2] + double(cz - r) * gs.h[2]));
+                if (cz + r < Gz - 1) bound = fmin(bound, (gs.lo[2] + double(cz + r + 1) * gs.h[2]) - qz);
+                const double bs = bound * (1.0 - 1e-9) - gs.slack;
+                if (bs > 0.0 && __longlong_as_double((long long)worst) < bs * bs) done = true;
+            }
         }
     }
 
-    int32_t *row = out + int64_t(i) * m;
-    for (int k = 0; k < m; ++k) row[k] = k < top.cnt ? top.ids[k * TQ] : -1;
+    if (has_q && sl < m) out[int64_t(i) * m + sl] = id == kNoId ? -1 : id;
 }
 
 __global__ void fill_rows_kernel(int32_t *p, int64_t count, int32_t v)
@@ -327,8 +363,6 @@ GridSpec make_grid(const nngp_handle *h, double nref, double lambda, int64_t max
     gs.slack = 1e-14 * mag;
     return gs;
 }
-
-inline size_t query_smem(int m) { return size_t(m) * TQ * (sizeof(double) + sizeof(int32_t)); }
 
 // handle-owned (scratch_get): a build costs no cudaMalloc / cudaFree after the first one
 struct Scratch {
@@ -398,10 +432,14 @@ cudaError_t launch_knn_grid(nngp_handle *h, bool ordered, int m, int64_t row_lo,
         if (std::max(lev[l].a, row_lo) < std::min(lev[l].b, row_hi)) any_level = true;
 
     const bool dim3 = h->D == 3;
-    auto qkern = ordered ? (dim3 ? knn_grid_query_kernel<true, true> : knn_grid_query_kernel<false, true>)
-                         : (dim3 ? knn_grid_query_kernel<true, false> : knn_grid_query_kernel<false, false>);
-    const size_t smem = query_smem(m);
-    GRID_TRY(cudaFuncSetAttribute(qkern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // lanes per query: the smallest sub-warp that holds the m list entries
+    const int sw = m <= 8 ? 8 : m <= 16 ? 16 : 32;
+    auto pick = [&](auto dim3_c, auto ordered_c) {
+        constexpr bool D3 = decltype(dim3_c)::value, ORD = decltype(ordered_c)::value;
+        return sw == 8 ? knn_grid_query_kernel<D3, ORD, 8> : sw == 16 ? knn_grid_query_kernel<D3, ORD, 16> : knn_grid_query_kernel<D3, ORD, 32>;
+    };
+    auto qkern = ordered ? (dim3 ? pick(std::true_type{}, std::true_type{}) : pick(std::false_type{}, std::true_type{}))
+                         : (dim3 ? pick(std::true_type{}, std::false_type{}) : pick(std::false_type{}, std::false_type{}));
     const bool partial = !window && (row_lo > 0 || row_hi < n);  // a window table has no rows outside [row_lo, row_hi)
     bool filled = false;
 
@@ -464,8 +502,9 @@ cudaError_t launch_knn_grid(nngp_handle *h, bool ordered, int m, int64_t row_lo,
                                                   sc.qlist);
         GRID_TRY(cudaGetLastError());
         const int nq = int(qhi - qlo);
-        qkern<<<(nq + TQ - 1) / TQ, TQ, smem, stream>>>(h->pts, sc.sorted, starts, sc.cell_of, sc.qlist, nq, gs, m,
-                                                        int(std::min<int64_t>(cand_cap, INT32_MAX)), table);
+        const int qpb = (QTHREADS / 32) * (32 / sw);  // queries per block
+        qkern<<<(nq + qpb - 1) / qpb, QTHREADS, 0, stream>>>(h->pts, sc.sorted, starts, sc.cell_of, sc.qlist, nq, gs, m,
+                                                             int(std::min<int64_t>(cand_cap, INT32_MAX)), table);
         GRID_TRY(cudaGetLastError());
         h->launches += 2;
     }

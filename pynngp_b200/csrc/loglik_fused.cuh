@@ -71,8 +71,13 @@ __device__ __forceinline__ float t_fma(float a, float b, float c) { return fmaf(
 
 // exp(t) = 2^k * 2^(j/2^TB) * e^r, |r| <= ln2/2^(TB+1): a table of 2^TB entries in shared memory and a
 // polynomial whose degree shrinks as the table grows (truncation < 4e-17 in all three):
-//   TB = 11 (16 KB) cubic    -- the unrolled shapes, whose blocks have shared memory to spare
-//   TB =  8 ( 2 KB) quartic  -- the rolled (8, 4) shape: 2 blocks/SM must still fit
+//   TB = 11 (16 KB) cubic    -- (round 1; a random 8-byte lookup of a 2048-entry table costs 5.2 shared-memory
+//                               wavefronts per warp -- 16 lanes of a half-warp into 16 bank pairs -- and the kernel is
+//                               bound by the shared-memory data stage: profiles/r2a_fused_smem.txt)
+//   TB =  8 quartic          -- the unrolled shapes: 16 COPIES of the 256 entries, copy c at [j * 16 + c], lane l
+//                               reads copy l % 16 (REP = 4, 32 KB).  Every lane of a half-warp owns one bank pair:
+//                               a lookup is conflict-free by construction, 2 wavefronts, for one more FMA per pair.
+//                               The rolled (8, 4) shape keeps a single copy (2 KB): 2 blocks/SM must still fit
 //   TB =  6 (512 B) quintic  -- the rolled (16, 3) shape
 template <int TB> __host__ __device__ constexpr int exp_slot() { return TB == 11 ? 2 : TB == 8 ? 1 : 0; }
 __constant__ double kExpA[3] = {-64.0 / 0.6931471805599453094, -256.0 / 0.6931471805599453094,
@@ -137,7 +142,7 @@ __device__ __forceinline__ float fast_rcp(float x)
 // sigma2 * exp(-u) for u >= 0.  fp64: table of sigma2 * 2^(j/2^TB) in shared memory (tab) + a short
 // polynomial -> 7 (TB = 11) to 9 (TB = 6) FP64 instructions.  u >= 708 (which includes the far-away
 // sentinel rows) returns exactly 0.
-template <int TB>
+template <int TB, int REP = 0>
 __device__ __forceinline__ double scaled_exp_neg(double u, const double *tab, double /*sigma2*/)
 {
     const double kd = fma(u, kExpA[exp_slot<TB>()], kCovC[2]);
@@ -151,13 +156,13 @@ __device__ __forceinline__ double scaled_exp_neg(double u, const double *tab, do
         q = fma(r, q, 0.5);
     }
     q = fma(r, q, 1.0);
-    const double tv = tab[ki & ((1 << TB) - 1)];
+    const double tv = tab[(ki & ((1 << TB) - 1)) << REP];  // REP > 0: tab already points at this lane's copy
     const double p = fma(tv * r, q, tv);                  // tv * (1 + r*q)
     const int hi = __double2hiint(p) + ((ki >> TB) << 20); // * 2^k
     const double v = __hiloint2double(hi, __double2loint(p));
     return __double2hiint(u) >= 0x40862000 ? 0.0 : v;
 }
-template <int TB>
+template <int TB, int REP = 0>
 __device__ __forceinline__ float scaled_exp_neg(float u, const float *, float sigma2)
 {
     // k = round(-u / ln2) by the magic-number add (1.5 * 2^23): the sum's low mantissa bits are k itself, so
@@ -174,10 +179,10 @@ __device__ __forceinline__ float scaled_exp_neg(float u, const float *, float si
 }
 
 // sigma2 * rho(u), u = phi * distance (oracle: nngp_oracle.c corr()).
-template <typename T, int KERN, int TB>
+template <typename T, int KERN, int TB, int REP = 0>
 __device__ __forceinline__ T cov_from_u(T u, const T *tab, T sigma2)
 {
-    const T e = scaled_exp_neg<TB>(u, tab, sigma2);
+    const T e = scaled_exp_neg<TB, REP>(u, tab, sigma2);
     if (KERN == NNGP_EXPONENTIAL) return e;
     if (KERN == NNGP_MATERN32) return t_fma(u, e, e);
     return t_fma(u, t_fma(u, T(1.0 / 3.0), T(1)), T(1)) * e;
@@ -206,7 +211,7 @@ __device__ __forceinline__ void sqrt_batch(double (&x)[B])
     for (int b = 0; b < B; ++b) x[b] = fma(t1[b], y0[b], t1[b]);
 }
 // x[b] = u_b >= 0  ->  x[b] = (table scale) * rho(u_b)
-template <int KERN, int B, int TB>
+template <int KERN, int B, int TB, int REP = 0>
 __device__ __forceinline__ void corr_batch(double (&x)[B], const double *tab)
 {
     double e[B], kd[B], r[B], qq[B], tv[B];
@@ -217,7 +222,7 @@ __device__ __forceinline__ void corr_batch(double (&x)[B], const double *tab)
 #pragma unroll
     for (int b = 0; b < B; ++b) { ki[b] = __double2loint(kd[b]); kd[b] = kd[b] - shift; }
 #pragma unroll
-    for (int b = 0; b < B; ++b) tv[b] = tab[ki[b] & ((1 << TB) - 1)];
+    for (int b = 0; b < B; ++b) tv[b] = tab[(ki[b] & ((1 << TB) - 1)) << REP];
 #pragma unroll
     for (int b = 0; b < B; ++b) r[b] = fma(kd[b], kExpB[exp_slot<TB>()], -x[b]);
     if (TB == 11) {
@@ -256,13 +261,13 @@ __device__ __forceinline__ void corr_batch(double (&x)[B], const double *tab)
         else x[b] = fma(x[b], fma(x[b], kCovC[8], 1.0), 1.0) * e[b];
     }
 }
-template <int KERN, int B, int TB>
+template <int KERN, int B, int TB, int REP = 0>
 __device__ __forceinline__ void cov_batch(double (&x)[B], const double *tab, double)
 {
     sqrt_batch<B>(x);
-    corr_batch<KERN, B, TB>(x, tab);
+    corr_batch<KERN, B, TB, REP>(x, tab);
 }
-template <int KERN, int B, int TB>
+template <int KERN, int B, int TB, int REP = 0>
 __device__ __forceinline__ void cov_batch(float (&x)[B], const float *tab, float sigma2)
 {
 #pragma unroll
@@ -406,7 +411,25 @@ struct WarpSmem {
     // location strides are padded by 16 bytes so the W groups of a warp start in different banks
     // (unpadded, all groups alias: 8-way conflicts on every record / coordinate access)
     static constexpr int rec_stride = P * 32 + 16;                        // bytes per location
-    static constexpr int stage_stride = P * int(sizeof(StagePt<T, DIM3>)) + 16;
+    // Staged (re-centred, scaled) coordinates.  fp64 in 3-D: {x, y} pairs and z in separate arrays (a 32-byte
+    // {x, y, z, pad} point makes every 16-byte store a 2-way bank conflict and every column read two 16-byte loads).
+    static constexpr bool SOA3 = DIM3 && sizeof(T) == 8;
+    static constexpr int pt_bytes = SOA3 ? 16 : int(sizeof(StagePt<T, DIM3>));
+    static constexpr int stage_stride = P * pt_bytes + 16;
+    // elements per location of the z array (SOA3) and of the elimination's column buffers: P entries, w_k, pad
+    static constexpr int col_stride = P + 2;
+    static constexpr size_t zbuf = SOA3 ? size_t(W) * col_stride * sizeof(T) : 0;
+    // Where location g of the warp sits inside those arrays.  The kernel is bound by the shared-memory data stage
+    // (profiles/r2a_fused_smem.txt), and with the W = 8 locations of a (4, R) shape in plain order the row-owner
+    // stores collide: an 8-byte store is processed half a warp at a time and its 4 locations' windows of 4 consecutive
+    // rows must tile the 32 banks, while an 8-byte broadcast load sees all 8 locations at once; a 16-byte store is
+    // processed a quarter-warp (2 locations) at a time, a 16-byte broadcast load half a warp.  With strides of 16 bytes
+    // (mod 128) the slot ORDER decides which locations meet: measured (tools/ubench/smem_layout.cu) 2.0 / 1.3 / 2.0
+    // wavefronts per column store / pivot load / column load with col_pos against 4.0 / 1.3 / 2.0 in plain order,
+    // and 4.6 / 2.0 per staged-point store / load with stage_pos against 8.0 / 2.0 -- the minima of these accesses.
+    static constexpr bool PERM = sizeof(T) == 8 && G == 4;
+    __host__ __device__ static constexpr int col_pos(int g) { return PERM ? (g & 3) * 2 + (g >> 2) : g; }
+    __host__ __device__ static constexpr int stage_pos(int g) { return PERM ? (g & 1) * 4 + (g >> 1) : g; }
     static constexpr size_t rec = size_t(W) * rec_stride;                 // gathered {x,y,z,yval} records
     static constexpr size_t e2 = DIM3 ? size_t(W) * P * sizeof(double) : 0;  // gathered eps2 (D = 3 only;
                                                                              // D < 3 records carry it in .z)
@@ -416,22 +439,24 @@ struct WarpSmem {
     static constexpr size_t acc = sweep_build<BUILD>() ? size_t(kSweepChunk) * 4 * 32 * sizeof(double) : size_t(3) * 32 * sizeof(double);
     static constexpr size_t tile = BUILD == 1 ? (size_t(W) * tile_stride<P>() * sizeof(T) + 15) / 16 * 16 : 0;  // pair-indexed tile
     // scaled coordinates during the build; the elimination's two column buffers afterwards
-    static constexpr int col_stride = P + 2;  // elements per location: P column entries, w_k, pad (distinct banks per group)
     static constexpr size_t colbuf = size_t(2) * W * col_stride * sizeof(T);
-    static constexpr size_t stage = (size_t(W) * stage_stride > colbuf ? size_t(W) * stage_stride : colbuf);
+    static constexpr size_t stage = (size_t(W) * stage_stride + zbuf > colbuf ? size_t(W) * stage_stride + zbuf : colbuf);
     static constexpr size_t dump = size_t(P) * P * sizeof(T);            // emit only: one location's factor
     __host__ __device__ static constexpr size_t total(bool emit) { return rec + e2 + idx + acc + tile + stage + (emit ? dump : 0); }
 };
 
 // block-shared part: exp table + the launch's pair list (one packed word per pair)
 template <int G, int BUILD>
-__host__ __device__ constexpr int exp_tab_bits() { return BUILD != 1 ? 11 : (G == 16 ? 6 : 8); }
+__host__ __device__ constexpr int exp_tab_bits() { return BUILD != 1 ? 8 : (G == 16 ? 6 : 8); }
+// log2 of the copies of the table (one per lane of a half-warp in the unrolled shapes)
+template <int G, int BUILD>
+__host__ __device__ constexpr int exp_rep_bits() { return BUILD != 1 ? 4 : 0; }
 // pairs evaluated in lock step by one lane: 8 in the rolled (8, 4) build, whose loop is bound by the
 // latency of its dependent shared-memory reads (pair list -> coordinates -> exp table)
 template <int G, int BUILD>
 __host__ __device__ constexpr int cov_batch_size() { return BUILD == 1 && G == 8 ? 8 : 4; }
 template <typename T, int G, int BUILD>
-__host__ __device__ constexpr size_t exp_tab_bytes() { return sizeof(T) == 8 ? (sizeof(double) << exp_tab_bits<G, BUILD>()) : 16; }  // fp32: no table
+__host__ __device__ constexpr size_t exp_tab_bytes() { return sizeof(T) == 8 ? (sizeof(double) << (exp_tab_bits<G, BUILD>() + exp_rep_bits<G, BUILD>())) : 16; }  // fp32: no table
 template <typename T, int G, int R, int BUILD>
 __host__ __device__ constexpr size_t block_smem()
 {
@@ -460,8 +485,9 @@ __global__ void __launch_bounds__(kThreads, MINB) fused_loglik_kernel(const __gr
     constexpr int P = G * R;   // rows of the augmented matrix
     constexpr int W = 32 / G;  // locations per warp
     static_assert(!FOLD || (R % 2 == 0 && ELIM == 1), "the folded layout pairs row blocks");
-    using Pt = StagePt<T, DIM3>;
     using WS = WarpSmem<T, G, R, DIM3, BUILD>;
+    constexpr bool SOA3 = WS::SOA3;          // 3-D fp64: z staged in its own array
+    using Pt = StagePt<T, DIM3 && !SOA3>;
 
     extern __shared__ __align__(32) unsigned char smem_raw[];
     TL(0, blockIdx.x == 0 && threadIdx.x == 0);
@@ -483,11 +509,12 @@ __global__ void __launch_bounds__(kThreads, MINB) fused_loglik_kernel(const __gr
     volatile double *accbuf = reinterpret_cast<volatile double *>(wbase + WS::rec + WS::e2 + WS::idx) + lane;
     T *tile_w = reinterpret_cast<T *>(wbase + WS::rec + WS::e2 + WS::idx + WS::acc);
     T *tile = tile_w + g * tile_stride<P>();  // this location's covariance entries
-    Pt *stage = reinterpret_cast<Pt *>(wbase + WS::rec + WS::e2 + WS::idx + WS::acc + WS::tile + g * WS::stage_stride);
+    Pt *stage = reinterpret_cast<Pt *>(wbase + WS::rec + WS::e2 + WS::idx + WS::acc + WS::tile + WS::stage_pos(g) * WS::stage_stride);
+    [[maybe_unused]] T *zstage = reinterpret_cast<T *>(wbase + WS::rec + WS::e2 + WS::idx + WS::acc + WS::tile + WS::W * WS::stage_stride) + WS::col_pos(g) * WS::col_stride;
     T *dump = reinterpret_cast<T *>(wbase + WS::rec + WS::e2 + WS::idx + WS::acc + WS::tile + WS::stage);
     // column buffers of the elimination: alias the staged coordinates (dead once the build is done)
     T *colw = reinterpret_cast<T *>(wbase + WS::rec + WS::e2 + WS::idx + WS::acc + WS::tile);
-    T *col_even = colw + g * WS::col_stride, *col_odd = colw + (W + g) * WS::col_stride;
+    T *col_even = colw + WS::col_pos(g) * WS::col_stride, *col_odd = colw + (W + WS::col_pos(g)) * WS::col_stride;
 
     constexpr bool SWEEP = sweep_build<BUILD>();
     static_assert(!SWEEP || (sizeof(T) == 8 && !EMIT && ELIM == 1), "the sweep variant is fp64, reduction only");
@@ -515,21 +542,23 @@ __global__ void __launch_bounds__(kThreads, MINB) fused_loglik_kernel(const __gr
         s_diag[1] = inv_s2;
     }
     const int m = a.m;
-    constexpr int TB = exp_tab_bits<G, BUILD>();
+    constexpr int TB = exp_tab_bits<G, BUILD>(), REP = exp_rep_bits<G, BUILD>();
     // (the sweep variant keeps the synchronous fill: its launches are long, and its register allocation is too
     // finely balanced to touch -- the asynchronous form cost it 10 % in spills)
-    constexpr bool ASYNC_TAB = FACT && TB == 11 && !SWEEP;
+    constexpr bool ASYNC_TAB = FACT && REP == 4 && TB == 8 && !SWEEP;
     if constexpr (sizeof(T) == 8) {
         if constexpr (ASYNC_TAB) {
-            // 16 KB, 16 bytes per cp.async, L2-only (every block reads the same lines); completes under the
-            // prologue's first wait_group, published to the block by the __syncthreads below
-            for (int k = threadIdx.x; k < (1 << TB) / 2; k += kThreads)
-                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr(exp_tab + 2 * k)), "l"(a.exp2tab + 2 * k) : "memory");
-        } else {  // sigma2 * 2^(k / 2^TB) from the handle's table of 2^(j/2048): one L2 load and a multiply
-            for (int k = threadIdx.x; k < (1 << TB); k += kThreads)
-                exp_tab[k] = T(double(sigma2) * __ldg(a.exp2tab + (k << (11 - TB))));
+            // 32 KB (the handle's replicated table, a.exp2tab + 2048), 16 bytes per cp.async, L2-only (every block
+            // reads the same lines); completes under the prologue's first wait_group, published to the block by
+            // the __syncthreads below
+            for (int k = threadIdx.x; k < (1 << (TB + REP)) / 2; k += kThreads)
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr(exp_tab + 2 * k)), "l"(a.exp2tab + 2048 + 2 * k) : "memory");
+        } else {  // sigma2 * 2^(j / 2^TB) from the handle's table of 2^(j/2048): one L2 load and a multiply
+            for (int k = threadIdx.x; k < (1 << (TB + REP)); k += kThreads)
+                exp_tab[k] = T(double(sigma2) * __ldg(a.exp2tab + ((k >> REP) << (11 - TB))));
         }
     }
+    const T *exp_lane = exp_tab + (REP ? (lane & ((1 << REP) - 1)) : 0);  // this lane's copy of the table
     // sum log F is carried as log(prod of mantissas) + ln2 * (sum of exponents): one multiply and a few
     // integer operations per location instead of a log() the whole warp would issue for one lane in G
     int nbad = 0;
@@ -671,7 +700,8 @@ __global__ void __launch_bounds__(kThreads, MINB) fused_loglik_kernel(const __gr
                 e2r[s] = T(e2);
                 Pt pt;
                 pt.x = rx[s]; pt.y = ry[s];
-                if constexpr (DIM3) { pt.z = rz[s]; pt.pad = T(0); }
+                if constexpr (SOA3) zstage[r] = rz[s];
+                else if constexpr (DIM3) { pt.z = rz[s]; pt.pad = T(0); }
                 stage[r] = pt;
             }
         }
@@ -721,9 +751,13 @@ __global__ void __launch_bounds__(kThreads, MINB) fused_loglik_kernel(const __gr
                         eoff[b] = pw.y;
                         const T dx = pa.x - pb.x, dy = pa.y - pb.y;
                         d2[b] = t_fma(dy, dy, t_fma(dx, dx, tiny_seed<T>()));
-                        if constexpr (DIM3) { const T dz = pa.z - pb.z; d2[b] = t_fma(dz, dz, d2[b]); }
+                        if constexpr (SOA3) {  // z entries are half the size of the {x, y} pairs: half the byte offset
+                            const unsigned char *zb = reinterpret_cast<const unsigned char *>(zstage);
+                            const T dz = *reinterpret_cast<const T *>(zb + ((pw.x & 0xffffu) >> 1)) - *reinterpret_cast<const T *>(zb + (pw.x >> 17));
+                            d2[b] = t_fma(dz, dz, d2[b]);
+                        } else if constexpr (DIM3) { const T dz = pa.z - pb.z; d2[b] = t_fma(dz, dz, d2[b]); }
                     }
-                    cov_batch<KERN, CB, TB>(d2, exp_tab, sigma2);
+                    cov_batch<KERN, CB, TB, REP>(d2, exp_lane, sigma2);
     #pragma unroll
                     for (int b = 0; b < CB; ++b) *reinterpret_cast<T *>(tb + eoff[b]) = d2[b];
                 }
@@ -758,6 +792,7 @@ __global__ void __launch_bounds__(kThreads, MINB) fused_loglik_kernel(const __gr
                     const SlotInfo si = slot_info<G, R, FOLD>(t);
                     T ax, ay, az;
                     Pt cj;
+                    [[maybe_unused]] T cz = T(0);
                     if (si.diag) {
                         // lanes q > tt: (row of block s, column j); the others: (row of block s1, column j1)
                         const bool first = q > si.tt;
@@ -765,13 +800,16 @@ __global__ void __launch_bounds__(kThreads, MINB) fused_loglik_kernel(const __gr
                         ay = first ? ry[si.s] : ry[si.s1];
                         az = first ? rz[si.s] : rz[si.s1];
                         cj = stage[first ? si.j : si.j1];
+                        if constexpr (SOA3) cz = zstage[first ? si.j : si.j1];
                     } else {
                         ax = rx[si.s]; ay = ry[si.s]; az = rz[si.s];
                         cj = stage[si.j];
+                        if constexpr (SOA3) cz = zstage[si.j];
                     }
                     const T dx = ax - cj.x, dy = ay - cj.y;
                     d2[b] = t_fma(dy, dy, t_fma(dx, dx, tiny_seed<T>()));
-                    if constexpr (DIM3) { const T dz = az - cj.z; d2[b] = t_fma(dz, dz, d2[b]); }
+                    if constexpr (SOA3) { const T dz = az - cz; d2[b] = t_fma(dz, dz, d2[b]); }
+                    else if constexpr (DIM3) { const T dz = az - cj.z; d2[b] = t_fma(dz, dz, d2[b]); }
                 }
                 if constexpr (SWEEP) {
                     // distances only: they serve every parameter vector of the chunk
@@ -781,7 +819,7 @@ __global__ void __launch_bounds__(kThreads, MINB) fused_loglik_kernel(const __gr
                         if (t0 + b < NP) Dst[t0 + b] = d2[b];
                     continue;
                 }
-                cov_batch<KERN, CB, TB>(d2, exp_tab, sigma2);
+                cov_batch<KERN, CB, TB, REP>(d2, exp_lane, sigma2);
 #pragma unroll
                 for (int b = 0; b < CB; ++b) {
                     if (t0 + b < NP) {
@@ -836,7 +874,7 @@ __global__ void __launch_bounds__(kThreads, MINB) fused_loglik_kernel(const __gr
                 T x[CBs];
 #pragma unroll
                 for (int b = 0; b < CBs; ++b) x[b] = Dst[(t0 + b < NP) ? t0 + b : NP - 1] * phik;
-                corr_batch<KERN, CBs, TB>(x, exp_tab);
+                corr_batch<KERN, CBs, TB, REP>(x, exp_lane);
 #pragma unroll
                 for (int b = 0; b < CBs; ++b) {
                     if (t0 + b < NP) {

@@ -310,10 +310,14 @@ int nngp_create(nngp_handle **out, int device, int dtype)
     if ((e = cudaMalloc(&h->d_tile_counter, sizeof(unsigned int))) != cudaSuccess) return bail(e, "cudaMalloc");
     if ((e = cudaMalloc(&h->d_viol, sizeof(int32_t))) != cudaSuccess) return bail(e, "cudaMalloc");
     {   // parameter-independent part of the covariance build's exp table: 2^(j/2048), j < 2048
-        std::vector<double> tab(2048);
+        // followed by the table the unrolled kernels copy into shared memory as it is: 2^(j/256), j < 256, in 16
+        // copies (copy c of entry j at [2048 + j * 16 + c]: one copy per lane of a half-warp, see loglik_fused.cuh)
+        std::vector<double> tab(2048 + 4096);
         for (int j = 0; j < 2048; ++j) tab[j] = exp2(double(j) / 2048.0);
-        if ((e = cudaMalloc(&h->d_exp2tab, sizeof(double) * 2048)) != cudaSuccess ||
-            (e = cudaMemcpy(h->d_exp2tab, tab.data(), sizeof(double) * 2048, cudaMemcpyHostToDevice)) != cudaSuccess)
+        for (int j = 0; j < 256; ++j)
+            for (int c = 0; c < 16; ++c) tab[2048 + j * 16 + c] = tab[j * 8];
+        if ((e = cudaMalloc(&h->d_exp2tab, sizeof(double) * tab.size())) != cudaSuccess ||
+            (e = cudaMemcpy(h->d_exp2tab, tab.data(), sizeof(double) * tab.size(), cudaMemcpyHostToDevice)) != cudaSuccess)
             return bail(e, "cudaMalloc");
     }
     *out = h;

@@ -67,7 +67,7 @@ struct nngp_handle {
     double *d_partials = nullptr;  // K_cap x grid_cap x 3
     unsigned int *d_counters = nullptr;  // K_cap tickets for the last-block reduction
     unsigned int *d_tile_counter = nullptr;
-    double *d_exp2tab = nullptr;   // 2^(j/2048), j < 2048 (built once at nngp_create)
+    double *d_exp2tab = nullptr;   // 2^(j/2048), j < 2048, then 16 copies of 2^(j/256), j < 256 (built once at nngp_create)
     double *h_stage = nullptr;     // pinned: K_cap x 4 parameter staging (K > NNGP_PV_MAX only)
     // results of the host-pointer calls land in MAPPED pinned host memory, written by the kernel's last
     // block itself, followed by a sequence stamp per blockIdx.y the host polls: no D2H copy, no stream sync
@@ -107,7 +107,7 @@ struct EvalArgs {
     const double *params;     // K x 4 (device), or NULL: the vectors are in pv[] (K <= NNGP_PV_MAX)
     double pv[NNGP_PV_MAX][NNGP_NPARAM];
     int K;                    // parameter vectors of this launch
-    const double *exp2tab;    // 2^(j/2048), j < 2048
+    const double *exp2tab;    // 2^(j/2048), j < 2048; [2048 + j * 16 + c] = 2^(j/256), j < 256, c < 16
     double *partials;         // gridDim.y x gridDim.x x 3
     unsigned int *counters;   // gridDim.y
     double *out;              // gridDim.y x 3 doubles in device memory, or NULL:
