@@ -90,7 +90,7 @@ def grid_knn_ordered(s, m, lam_scale=1.0, brute_rows=128, stats=None):
     lam = max(1.0, lam_scale * (m + 2.0 * math.sqrt(m)) / BALL[deff])
     a = T0
     while a < n:
-        b = min(2 * a, n)
+        b = min(max(2 * a, 4096 if a == T0 else 0), n)  # the lowest level runs up to 4096 (knn_grid.cu)
         gs = make_grid(bb_lo, bb_hi, D, float(a), lam, max(8 * n, 1024))
         G = gs["G"]
         cc = cell_coords(gs, pts[:b])

@@ -418,8 +418,10 @@ cudaError_t launch_knn_grid(nngp_handle *h, bool ordered, int m, int64_t row_lo,
     Level lev[40];
     int nlev = 0;
     if (ordered) {
+        // (the lowest level runs from the brute-force rows up to 4096: a few thousand queries over a few thousand
+        // points cost microseconds on any grid, a level's four launches do not)
         for (int64_t a = T0; a < n;) {
-            const int64_t b = std::min<int64_t>(2 * a, n);
+            const int64_t b = std::min<int64_t>(std::max<int64_t>(2 * a, a == T0 ? 4096 : 0), n);
             lev[nlev++] = Level{a, b};
             a = b;
         }

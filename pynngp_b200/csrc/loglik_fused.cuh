@@ -405,7 +405,7 @@ __host__ __device__ constexpr int tile_stride() { return (P * (P - 1) / 2 + 7) /
 
 // Per-warp shared-memory carve-up (bytes).  Everything a warp touches is private to it, so the
 // main loop needs __syncwarp only.
-template <typename T, int G, int R, bool DIM3, int BUILD>
+template <typename T, int G, int R, bool DIM3, int BUILD, int ELIM = 1>
 struct WarpSmem {
     static constexpr int P = G * R, W = 32 / G;
     // location strides are padded by 16 bytes so the W groups of a warp start in different banks
@@ -418,7 +418,7 @@ struct WarpSmem {
     static constexpr int stage_stride = P * pt_bytes + 16;
     // elements per location of the z array (SOA3) and of the elimination's column buffers: P entries, w_k, pad
     static constexpr int col_stride = P + 2;
-    static constexpr size_t zbuf = SOA3 ? size_t(W) * col_stride * sizeof(T) : 0;
+    static constexpr size_t zbuf = SOA3 ? size_t(sizeof(T) == 8 && G == 8 ? 6 : W) * col_stride * sizeof(T) : 0;
     // Where location g of the warp sits inside those arrays.  The kernel is bound by the shared-memory data stage
     // (profiles/r2a_fused_smem.txt), and with the W = 8 locations of a (4, R) shape in plain order the row-owner
     // stores collide: an 8-byte store is processed half a warp at a time and its 4 locations' windows of 4 consecutive
@@ -427,8 +427,11 @@ struct WarpSmem {
     // (mod 128) the slot ORDER decides which locations meet: measured (tools/ubench/smem_layout.cu) 2.0 / 1.3 / 2.0
     // wavefronts per column store / pivot load / column load with col_pos against 4.0 / 1.3 / 2.0 in plain order,
     // and 4.6 / 2.0 per staged-point store / load with stage_pos against 8.0 / 2.0 -- the minima of these accesses.
-    static constexpr bool PERM = sizeof(T) == 8 && G == 4;
-    __host__ __device__ static constexpr int col_pos(int g) { return PERM ? (g & 3) * 2 + (g >> 2) : g; }
+    // (G = 8, W = 4: the two locations of a half-warp 64 bytes apart (mod 128) for the column stores -- slots 0, 4, 1, 5
+    // of 6; its staged points are fine in plain order.)
+    static constexpr bool PERM = sizeof(T) == 8 && G == 4, PERM8 = sizeof(T) == 8 && G == 8;
+    static constexpr int col_slots = PERM8 ? 6 : W;
+    __host__ __device__ static constexpr int col_pos(int g) { return PERM ? (g & 3) * 2 + (g >> 2) : PERM8 ? (g & 1) * 4 + (g >> 1) : g; }
     __host__ __device__ static constexpr int stage_pos(int g) { return PERM ? (g & 1) * 4 + (g >> 1) : g; }
     static constexpr size_t rec = size_t(W) * rec_stride;                 // gathered {x,y,z,yval} records
     static constexpr size_t e2 = DIM3 ? size_t(W) * P * sizeof(double) : 0;  // gathered eps2 (D = 3 only;
@@ -439,7 +442,7 @@ struct WarpSmem {
     static constexpr size_t acc = sweep_build<BUILD>() ? size_t(kSweepChunk) * 4 * 32 * sizeof(double) : size_t(3) * 32 * sizeof(double);
     static constexpr size_t tile = BUILD == 1 ? (size_t(W) * tile_stride<P>() * sizeof(T) + 15) / 16 * 16 : 0;  // pair-indexed tile
     // scaled coordinates during the build; the elimination's two column buffers afterwards
-    static constexpr size_t colbuf = size_t(2) * W * col_stride * sizeof(T);
+    static constexpr size_t colbuf = size_t(2) * col_slots * col_stride * sizeof(T);
     static constexpr size_t stage = (size_t(W) * stage_stride + zbuf > colbuf ? size_t(W) * stage_stride + zbuf : colbuf);
     static constexpr size_t dump = size_t(P) * P * sizeof(T);            // emit only: one location's factor
     __host__ __device__ static constexpr size_t total(bool emit) { return rec + e2 + idx + acc + tile + stage + (emit ? dump : 0); }
@@ -464,10 +467,10 @@ __host__ __device__ constexpr size_t block_smem()
 }
 
 // dynamic shared memory needed by one block
-template <typename T, int G, int R, bool DIM3, int BUILD>
+template <typename T, int G, int R, bool DIM3, int BUILD, int ELIM = 1>
 constexpr size_t smem_bytes(bool emit)
 {
-    return block_smem<T, G, R, BUILD>() + size_t(kWarps) * WarpSmem<T, G, R, DIM3, BUILD>::total(emit);
+    return block_smem<T, G, R, BUILD>() + size_t(kWarps) * WarpSmem<T, G, R, DIM3, BUILD, ELIM>::total(emit);
 }
 
 template <typename T> struct Pair2;
@@ -485,7 +488,7 @@ __global__ void __launch_bounds__(kThreads, MINB) fused_loglik_kernel(const __gr
     constexpr int P = G * R;   // rows of the augmented matrix
     constexpr int W = 32 / G;  // locations per warp
     static_assert(!FOLD || (R % 2 == 0 && ELIM == 1), "the folded layout pairs row blocks");
-    using WS = WarpSmem<T, G, R, DIM3, BUILD>;
+    using WS = WarpSmem<T, G, R, DIM3, BUILD, ELIM>;
     constexpr bool SOA3 = WS::SOA3;          // 3-D fp64: z staged in its own array
     using Pt = StagePt<T, DIM3 && !SOA3>;
 
@@ -514,7 +517,7 @@ __global__ void __launch_bounds__(kThreads, MINB) fused_loglik_kernel(const __gr
     T *dump = reinterpret_cast<T *>(wbase + WS::rec + WS::e2 + WS::idx + WS::acc + WS::tile + WS::stage);
     // column buffers of the elimination: alias the staged coordinates (dead once the build is done)
     T *colw = reinterpret_cast<T *>(wbase + WS::rec + WS::e2 + WS::idx + WS::acc + WS::tile);
-    T *col_even = colw + WS::col_pos(g) * WS::col_stride, *col_odd = colw + (W + WS::col_pos(g)) * WS::col_stride;
+    T *col_even = colw + WS::col_pos(g) * WS::col_stride, *col_odd = colw + (WS::col_slots + WS::col_pos(g)) * WS::col_stride;
 
     constexpr bool SWEEP = sweep_build<BUILD>();
     static_assert(!SWEEP || (sizeof(T) == 8 && !EMIT && ELIM == 1), "the sweep variant is fp64, reduction only");
@@ -639,10 +642,21 @@ __global__ void __launch_bounds__(kThreads, MINB) fused_loglik_kernel(const __gr
                 const int slot = g * P + rowq(s);
                 const uint32_t dst = smem_addr(recbuf + rowq(s) * 32);
                 const double4 *src = a.pts + nidx[s];
-                asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
-                asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst + 16u),
-                             "l"(reinterpret_cast<const char *>(src) + 16)
-                             : "memory");
+                // Records that fit the L2 are gathered through the L1 (.ca: the second half of a record hits the sector
+                // its first half brought in).  When the records are several times the L2 most gathers come from HBM and
+                // allocating their lines in the L1 only evicts what the block still needs: .cg then (measured: cfg3
+                // 0.397 ms with .ca against 0.417 with .cg; cfg4 25.8 ms with .ca against 24.1 with .cg).
+                if (a.gather_bypass_l1) {
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 16u),
+                                 "l"(reinterpret_cast<const char *>(src) + 16)
+                                 : "memory");
+                } else {
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst + 16u),
+                                 "l"(reinterpret_cast<const char *>(src) + 16)
+                                 : "memory");
+                }
                 if (DIM3 && a.eps2)
                     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_addr(e2buf + slot)),
                                  "l"(a.eps2 + nidx[s])
@@ -1153,7 +1167,7 @@ cudaError_t launch_one(const EvalArgs &a, int K, int grid_x, cudaStream_t stream
     auto kern = fused_loglik_kernel<T, G, R, KERN, DIM3, MINB, BUILD, ELIM, false, FOLD>;
     if constexpr (!sweep_build<BUILD>())
         if (a.emit) kern = fused_loglik_kernel<T, G, R, KERN, DIM3, MINB, BUILD, ELIM, true, FOLD>;
-    const size_t smem = smem_bytes<T, G, R, DIM3, BUILD>(a.emit != 0);
+    const size_t smem = smem_bytes<T, G, R, DIM3, BUILD, ELIM>(a.emit != 0);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
 #ifdef NNGP_TUNE
@@ -1169,7 +1183,7 @@ int blocks_per_sm()
 {
     auto kern = fused_loglik_kernel<T, G, R, KERN, DIM3, MINB, BUILD, ELIM, false, FOLD>;
     int nb = 0;
-    const size_t smem = smem_bytes<T, G, R, DIM3, BUILD>(false);
+    const size_t smem = smem_bytes<T, G, R, DIM3, BUILD, ELIM>(false);
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, kThreads, smem) != cudaSuccess) nb = 1;
     return nb < 1 ? 1 : nb;
@@ -1221,6 +1235,9 @@ auto dispatch_shape(int m, const F &f)
             if (!strcmp(e, "44f")) return f.template run<4, 4, DIM3, 2, 2, 1, 1>();   // folded, 6-pair batches
             if (!strcmp(e, "44g")) return f.template run<4, 4, DIM3, 2, 2, 1, 2>();   // folded, row-block-major slots
             if (!strcmp(e, "44f4")) return f.template run<4, 4, DIM3, 2, 0, 1, 1>();  // folded, 4-pair batches
+            if (!strcmp(e, "44f9")) return f.template run<4, 4, DIM3, 2, 3, 1, 1>();  // folded, 9-pair batches
+            if (!strcmp(e, "44f3")) return f.template run<4, 4, DIM3, 3, 2, 1, 1>();  // folded, 6-pair batches, 12 warps/SM
+            if (!strcmp(e, "44f34")) return f.template run<4, 4, DIM3, 3, 0, 1, 1>(); // folded, 4-pair batches, 12 warps/SM
             if (!strcmp(e, "82f3")) return f.template run<8, 2, DIM3, 3, 2, 1, 1>();  // 8 lanes x 2 rows, 12 warps/SM
         }
         if (const char *e = getenv("NNGP_TUNE_SHAPE"); e && m > 15 && m <= 31 && !f.sweep()) {
@@ -1230,6 +1247,8 @@ auto dispatch_shape(int m, const F &f)
             if (!strcmp(e, "84f6")) return f.template run<8, 4, DIM3, 2, 2, 1, 1>();  // 6-pair batches
             if (!strcmp(e, "84r")) return f.template run<8, 4, DIM3, 2, 1, 1, 0>();   // rolled pair-list build
             if (!strcmp(e, "162f")) return f.template run<16, 2, DIM3, 2, 2, 1, 1>();
+            if (!strcmp(e, "162f3")) return f.template run<16, 2, DIM3, 3, 2, 1, 1>();
+            if (!strcmp(e, "162f34")) return f.template run<16, 2, DIM3, 3, 0, 1, 1>();
             if (!strcmp(e, "162g")) return f.template run<16, 2, DIM3, 2, 2, 1, 2>();
             if (!strcmp(e, "162f4")) return f.template run<16, 2, DIM3, 2, 0, 1, 1>();
             if (!strcmp(e, "162g4")) return f.template run<16, 2, DIM3, 2, 0, 1, 2>();
@@ -1241,6 +1260,7 @@ auto dispatch_shape(int m, const F &f)
         if (m <= 7 && f.sweep()) return f.template run<4, 2, DIM3, 4, 6, kElim, 1>();
         if (m <= 15 && f.sweep()) return f.template run<4, 4, DIM3, 2, 6, kElim, 1>();
         if (m <= 31 && f.sweep()) return f.template run<16, 2, DIM3, 2, 6, kElim, 1>();
+
         // fp64 single vector: the folded layouts (measured, tools/tune.py: DESIGN.md 5.3)
         if (m <= 7) return f.template run<4, 2, DIM3, 4, 0, kElim, 1>();
         if (m <= 15) return f.template run<4, 4, DIM3, 2, 2, kElim, 1>();

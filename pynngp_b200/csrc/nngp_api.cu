@@ -177,6 +177,7 @@ int launch_eval(nngp_handle *h, int kernel_id, const double *d_params, const dou
     if (!d_params) memcpy(a.pv, pv, sizeof(double) * NNGP_NPARAM * K);
     a.partials = h->d_partials; a.counters = h->d_counters; a.out = d_out; a.hout = hout; a.seq = seq;
     a.emit = 0; a.exp2tab = h->d_exp2tab; a.K = K;
+    a.gather_bypass_l1 = h->n * int64_t(sizeof(double4)) > (int64_t(96) << 20);  // records beyond ~ the L2's size
     if (px) a.px = *px;
     if (h->timing) CUDA_TRY(h, cudaEventRecord(h->ev0, st));
     CUDA_TRY(h, family_launch(h->dtype, kernel_id, h->m, h->D, a, K, grid, st));

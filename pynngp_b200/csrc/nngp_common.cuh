@@ -46,7 +46,7 @@ struct nngp_handle {
     bool bb_finite = false;                              // every coordinate finite
     double knn_lambda_scale = 1.0;                       // grid k-NN: cell occupancy multiplier
     int knn_used_grid = 0;                               // last stage-1 build went through the grid
-    int64_t knn_brute_rows = 4096;                       // grid k-NN: rows below this use brute force
+    int64_t knn_brute_rows = 128;                        // grid k-NN: rows below this use brute force
 
     double4 *pts = nullptr;
     double *d_ystage = nullptr;  // n doubles: landing buffer of nngp_set_y (allocated on first use)
@@ -114,6 +114,7 @@ struct EvalArgs {
     uint4 *hout;              //   gridDim.y x 3 self-stamped 16-byte lines in MAPPED pinned host memory (ll_store)
     unsigned int seq;         //   the stamp of this evaluation
     // optional per-location outputs (rows lo..hi map to output rows 0..hi-lo); any may be null
+    int gather_bypass_l1;     // records >> L2: gather them with cp.async.cg (see loglik_fused.cuh issue_rec)
     int emit;                 // 0: reduction only
     double *B, *F, *CN, *cc, *cs;
     PeerExchange px;          // world > 1: `out` receives the sum over all ranks (see peer_allreduce3)

@@ -3,7 +3,7 @@
 # Usage: gpurun -- bash tools/gpu_iter.sh TAG [noncu]
 TAG=${1:-it}
 mkdir -p gpurun_out
-if [ -x tools/ubench/smem_layout ]; then tools/ubench/smem_layout 4 4 8 0 288 576 144; tools/ubench/smem_layout 4 4 16 0 1088 272 544; fi
+
 timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/${TAG}_pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -15 gpurun_out/${TAG}_pytest_gpu.log
 timeout 900 python bench.py --steps 30 --warmup 5 --cpu-seconds 2 > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err; echo "bench rc=$?"
 python - <<PY

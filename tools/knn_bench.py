@@ -17,7 +17,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("cfg")
 ap.add_argument("--brute", action="store_true")
 ap.add_argument("--lams", default="1.0")
-ap.add_argument("--rows", default="8192")
+ap.add_argument("--rows", default="128")
 ap.add_argument("--n", type=int, default=0)
 a = ap.parse_args()
 c = CONFIGS[a.cfg]

@@ -5,7 +5,10 @@ import sys
 import numpy as np
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from pynngp_b200 import _lib  # noqa: E402
+from pynngp_b200 import _lib, build as _build  # noqa: E402
+
+if os.environ.get("NNGP_TUNE_SHAPE"):  # development library: the shape knob selects the kernel variant under the profiler
+    _lib.LIB_PATH = _build.TUNE_LIB
 from pynngp_b200.synthetic import CONFIGS, PARAMS, synthetic  # noqa: E402
 
 name = sys.argv[1] if len(sys.argv) > 1 else "cfg3"
