@@ -216,10 +216,17 @@ def run_ours(args, cfg):
         # NCCL's own messages (its version banner under NCCL_DEBUG=VERSION/INFO) go to stderr: stdout carries
         # the one JSON line and nothing else
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-        warm = torch.zeros(1, device="cuda")
-        dist.all_reduce(warm)  # the communicator is created here, outside every timed or reported region
-        torch.cuda.synchronize()
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)  # the banner is written to file descriptor 1 by the library itself: park it on stderr
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+            warm = torch.zeros(1, device="cuda")
+            dist.all_reduce(warm)  # the communicator is created here, outside every timed or reported region
+            torch.cuda.synchronize()
+        finally:
+            os.dup2(saved_stdout, 1)
+            os.close(saved_stdout)
     ngpu = args.gpus
     devices = list(range(ngpu)) if single_process else local
 
