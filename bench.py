@@ -481,17 +481,21 @@ def run_ours(args, cfg):
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     hbm_ach = nloc * hbm_bytes_per_location(cfg["m"], cfg["D"]) / (kern_ms * 1e-3) / 1e9
-    traffic, traffic_source = None, None
+    traffic, traffic_source, units_seen = None, None, None
     tr_path = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tr_path) and args.config == "cfg3" and ngpu == 1 and args.dtype == "float64":
         tr = json.load(open(tr_path))
         traffic = tr.get("fused_dram_bytes_per_launch")
+        # the same capture's view of the units the kernel loads (constants, like `traffic`): the shared-memory data
+        # stage runs closer to its peak than the FP64 pipe the roofline is quoted against
+        units_seen = {k: tr.get(k) for k in ("smem_data_stage_pct_of_peak", "smem_wavefronts_per_launch", "fp64_pipe_pct_active",
+                                             "issue_slots_pct_active")}
         traffic_source = ("constant read from profiles/traffic.json: dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` "
                           f"capture of this workload's kernel ({tr.get('source', 'see profiles/README.md')}); not measured in this run")
     roofline = {
         "bound": "fp64" if args.dtype == "float64" else "fp32",
         "achieved": achieved_tflops, "peak": peak_tflops, "unit": "TFLOP/s", "frac": achieved_tflops / peak_tflops,
-        "traffic": traffic, "traffic_source": traffic_source,
+        "traffic": traffic, "traffic_source": traffic_source, "ncu_units": units_seen,
         "kernel": "nngp_fused::fused_loglik_kernel", "kernel_ms": kern_ms,
         "algorithmic_instr_per_location": ipl, "locations_per_launch": nloc,
         "peak_source": "measured here: register-resident FMA chains, nngp_measure_fma_peak (no vector-pipe figure in MEASURED_PEAKS.json)",

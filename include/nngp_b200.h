@@ -120,7 +120,7 @@ int nngp_neighbor_window(const nngp_handle *h, int64_t *row0, int64_t *rows);
  * the path); nngp_factors over the same rows then returns the kriging weights and variances. */
 int nngp_build_neighbors_capped(nngp_handle *h, int m, int64_t row_lo, int64_t row_hi, int64_t cand_cap, int algo);
 /* Grid search knobs: cells hold lambda_scale * (m + 2 sqrt m) / unit-ball-volume usable points
- * (default 1.0); rows below brute_rows (default 128) always use brute force. */
+ * (default 0.5); rows below brute_rows (default 128) always use brute force. */
 int nngp_set_knn_tuning(nngp_handle *h, double lambda_scale, int64_t brute_rows);
 /* 1 if the last nngp_build_neighbors_grid call went through the grid, 0 if it fell back. */
 int nngp_knn_used_grid(const nngp_handle *h);

@@ -208,7 +208,7 @@ class Engine:
                     "nngp_build_neighbors_capped")
         self.m = int(m)
 
-    def set_knn_tuning(self, lambda_scale=1.0, brute_rows=128):
+    def set_knn_tuning(self, lambda_scale=0.5, brute_rows=128):
         self._check(self._lib.nngp_set_knn_tuning(self._h, float(lambda_scale), int(brute_rows)), "nngp_set_knn_tuning")
 
     def knn_used_grid(self):

@@ -69,7 +69,9 @@ TUNE_LIB = os.path.join(OUT_DIR, "libnngp_b200_tune.so")
 def build_tune(force=False):
     """The DEVELOPMENT library tools/tune.py loads explicitly: same sources with NNGP_TUNE (extra kernel shapes selected
     by NNGP_TUNE_SHAPE).  The product library never contains those knobs."""
-    return build(force=force, lib=TUNE_LIB, obj_dir=os.path.join(OUT_DIR, "obj_tune"), defines=("NNGP_TUNE",))
+    # NNGP_DEV_DEFINES=A,B replaces the default define set (e.g. NNGP_DIRECT alone: one experiment, a fast build)
+    defines = tuple(d for d in os.environ.get("NNGP_DEV_DEFINES", "NNGP_TUNE").split(",") if d)
+    return build(force=force, lib=TUNE_LIB, obj_dir=os.path.join(OUT_DIR, "obj_tune"), defines=defines)
 
 
 def build(force=False, verbose=False, lib=LIB, obj_dir=OBJ_DIR, defines=()):

@@ -83,15 +83,17 @@ __global__ void __launch_bounds__(1024) scan_cells_kernel(const int *counts, int
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     int running = 0;
     double sq = 0.0;
-    for (int base = 0; base < ncell; base += 1024 * 4) {
-        const int k0 = base + tid * 4;
-        int v[4];
+    constexpr int IPT = 16;  // cells per thread and round: a round costs three block barriers whatever it scans
+    for (int base = 0; base < ncell; base += 1024 * IPT) {
+        const int k0 = base + tid * IPT;
+        int v[IPT];
+        int s = 0;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
+        for (int k = 0; k < IPT; ++k) {
             v[k] = k0 + k < ncell ? in[k0 + k] : 0;
             sq += double(v[k]) * double(v[k]);
+            s += v[k];
         }
-        const int s = v[0] + v[1] + v[2] + v[3];
         int incl = s;
 #pragma unroll
         for (int off = 1; off < 32; off <<= 1) {
@@ -114,7 +116,7 @@ __global__ void __launch_bounds__(1024) scan_cells_kernel(const int *counts, int
         __syncthreads();
         int pre = running + warp_tot[wid] + incl - s;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
+        for (int k = 0; k < IPT; ++k) {
             if (k0 + k < ncell) { st[k0 + k] = pre; cu[k0 + k] = pre; }
             pre += v[k];
         }

@@ -44,7 +44,7 @@ struct nngp_handle {
     int64_t lo = 0, hi = 0;
     double bb_lo[3] = {0, 0, 0}, bb_hi[3] = {0, 0, 0};  // bounding box of the coordinates (set_data)
     bool bb_finite = false;                              // every coordinate finite
-    double knn_lambda_scale = 1.0;                       // grid k-NN: cell occupancy multiplier
+    double knn_lambda_scale = 0.5;                       // grid k-NN: cell occupancy multiplier
     int knn_used_grid = 0;                               // last stage-1 build went through the grid
     int64_t knn_brute_rows = 128;                        // grid k-NN: rows below this use brute force
 

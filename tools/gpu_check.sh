@@ -23,3 +23,7 @@ timeout 900 ncu --set full --clock-control none --import-source on -k regex:fuse
     python tools/prof_driver.py cfg4 float64 2 2000000 > gpurun_out/${TAG}_ncu_fused_m30.log 2>&1; echo "ncu fused m30 rc=$?"
 fi
 ls -la gpurun_out | tail -20
+if [ "$2" != "noncu" ]; then
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:knn_grid_query -c 8 -f -o gpurun_out/${TAG}_prof_knn \
+    python tools/prof_driver.py cfg3 float64 1 > gpurun_out/${TAG}_ncu_knn.log 2>&1; echo "ncu knn rc=$?"
+fi

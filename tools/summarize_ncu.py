@@ -20,6 +20,7 @@ keys = [
     "TPC.TriageCompute.sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed",
     "dram__bytes_read.sum", "dram__bytes_write.sum", "dram__throughput.avg.pct_of_peak_sustained_elapsed",
     "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "lts__t_bytes.sum", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum",
+    "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed",
     "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "smsp__warps_eligible.avg.per_cycle_active",
     "sm__cycles_elapsed.avg", "sm__cycles_elapsed.avg.per_second",
 ]
@@ -46,5 +47,11 @@ for d in summ:
         scale = {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1}
         rd = float(d["dram__bytes_read.sum"][0]) * scale[d["dram__bytes_read.sum"][1]]
         wr = float(d["dram__bytes_write.sum"][0]) * scale[d["dram__bytes_write.sum"][1]]
-        json.dump({"fused_dram_bytes_per_launch": rd + wr, "read": rd, "write": wr, "source": rep},
+        smem = d.get("l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", ("", ""))[0]
+        smem_pct = d.get("l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed", ("", ""))[0]
+        json.dump({"fused_dram_bytes_per_launch": rd + wr, "read": rd, "write": wr, "source": rep,
+                   "smem_wavefronts_per_launch": float(smem) if smem else None,
+                   "smem_data_stage_pct_of_peak": float(smem_pct) if smem_pct else None,
+                   "fp64_pipe_pct_active": float(d["sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active"][0]),
+                   "issue_slots_pct_active": float(d["smsp__issue_active.avg.pct_of_peak_sustained_active"][0])},
                   open(out_prefix + "_traffic.json", "w"))
