@@ -916,7 +916,11 @@ __global__ void __launch_bounds__(kThreads, MINB) fused_loglik_kernel(const __gr
                     if (s * G + G - 1 >= k) col[rowq(s)] = A[s][k];
                 if (rowq(k / G) == k) col[P] = w[k / G];
                 __syncwarp();
-                const T Dk = col[k], wk = col[P];
+                // even k: the 16-byte load of the pair (k, k + 1) that the trailing update needs anyway carries D_k in its
+                // first half (an 8-byte load of col[k] alone would be one more wavefront on the data stage)
+                T2 first = {T(0), T(0)};
+                if ((k & 1) == 0) first = *reinterpret_cast<const T2 *>(col + k);
+                const T Dk = (k & 1) == 0 ? first.x : col[k], wk = col[P];
                 bad |= !(Dk > T(0));
                 if (k == P - 1) {
                     Flast = Dk;
@@ -934,7 +938,7 @@ __global__ void __launch_bounds__(kThreads, MINB) fused_loglik_kernel(const __gr
 #pragma unroll
                     for (int j0 = 0; j0 < P; j0 += 2) {
                         if (j0 + 1 > k) {
-                            const T2 uu = *reinterpret_cast<const T2 *>(col + j0);  // broadcast inside the group
+                            const T2 uu = j0 == k ? first : *reinterpret_cast<const T2 *>(col + j0);  // broadcast inside the group
                             if (j0 > k) {
 #pragma unroll
                                 for (int s = 0; s < R; ++s)
