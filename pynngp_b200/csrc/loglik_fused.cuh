@@ -217,6 +217,11 @@ __device__ __forceinline__ void corr_batch(double (&x)[B], const double *tab)
     double e[B], kd[B], r[B], qq[B], tv[B];
     int ki[B];
     const double shift = kCovC[2];  // second constant of a two-constant FMA: a register
+    // u is capped at 700 through its high word (one integer min; u >= 0): the exponent arithmetic below then never
+    // leaves the normal range -- far-away sentinel rows included -- and e^-u bottoms out at 1e-304 instead of 0,
+    // which no covariance can tell from 0.  (A compare and two selects on the result cost two more issue slots per pair.)
+#pragma unroll
+    for (int b = 0; b < B; ++b) x[b] = __hiloint2double(min(__double2hiint(x[b]), 0x4085E000), __double2loint(x[b]));
 #pragma unroll
     for (int b = 0; b < B; ++b) kd[b] = fma(x[b], kExpA[exp_slot<TB>()], shift);
 #pragma unroll
@@ -252,7 +257,7 @@ __device__ __forceinline__ void corr_batch(double (&x)[B], const double *tab)
     for (int b = 0; b < B; ++b) {
         const int hi = __double2hiint(r[b]) + ((ki[b] >> TB) << 20);
         const double v = __hiloint2double(hi, __double2loint(r[b]));
-        e[b] = __double2hiint(x[b]) >= 0x40862000 ? 0.0 : v;
+        e[b] = v;
     }
 #pragma unroll
     for (int b = 0; b < B; ++b) {
@@ -274,7 +279,8 @@ __device__ __forceinline__ void cov_batch(float (&x)[B], const float *tab, float
     for (int b = 0; b < B; ++b) x[b] = cov_from_u<float, KERN, TB>(fast_sqrt(x[b]), tab, sigma2);
 }
 
-// far-away sentinel for padded rows: every covariance with it underflows to exactly 0
+// far-away sentinel for padded rows: every covariance with it underflows (fp32: to exactly 0; fp64: to ~1e-304, the
+// floor of the batch exponential, which no pivot or sum can tell from 0)
 template <typename T> __device__ __forceinline__ T sentinel_coord(int r);
 template <> __device__ __forceinline__ double sentinel_coord<double>(int r) { return 1e100 * double(r + 1); }
 template <> __device__ __forceinline__ float sentinel_coord<float>(int r) { return 1e15f * float(r + 1); }
@@ -704,7 +710,7 @@ __global__ void __launch_bounds__(kThreads, MINB) fused_loglik_kernel(const __gr
                     if (!DIM3) e2 = v1.x;  // D < 3: the record's z slot carries eps2
                     else if (a.eps2) e2 = e2buf[g * P + r];
                 }
-                // padded rows sit at a far-away sentinel: all their covariances are exactly 0
+                // padded rows sit at a far-away sentinel: all their covariances vanish (see sentinel_coord)
                 rx[s] = valid[s] ? T((v0.x - sx) * phi) : sentinel_coord<T>(r);
                 ry[s] = valid[s] ? T((v0.y - sy) * phi) : T(0);
                 rz[s] = valid[s] ? T((v1.x - sz) * phi) : T(0);
@@ -856,7 +862,10 @@ __global__ void __launch_bounds__(kThreads, MINB) fused_loglik_kernel(const __gr
 #pragma unroll
                 for (int j = 0; j < P; ++j) {
                     if (j >= (s + 1) * G || j > r) continue;
-                    const double v = valid[s] ? double(A[s][j]) : 0.0;
+                    // a padded row or column reports exactly 0 (the build itself leaves ~1e-304 there: its exponent
+                    // arithmetic caps u at 700); a padded column is recognised by its staged sentinel coordinate
+                    const bool col_valid = j == r || double(stage[j].x) < (sizeof(T) == 8 ? 1e99 : 1e14);
+                    const double v = valid[s] && col_valid ? double(A[s][j]) : 0.0;
                     if (r == P - 1) {
                         if (j < m && a.cc) a.cc[o * m + j] = v;
                         if (j == P - 1 && a.cs) a.cs[o] = v;
