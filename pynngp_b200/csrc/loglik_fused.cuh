@@ -1252,6 +1252,9 @@ auto dispatch_shape(int m, const F &f)
             if (!strcmp(e, "44f3")) return f.template run<4, 4, DIM3, 3, 2, 1, 1>();  // folded, 6-pair batches, 12 warps/SM
             if (!strcmp(e, "44f34")) return f.template run<4, 4, DIM3, 3, 0, 1, 1>(); // folded, 4-pair batches, 12 warps/SM
             if (!strcmp(e, "82f3")) return f.template run<8, 2, DIM3, 3, 2, 1, 1>();  // 8 lanes x 2 rows, 12 warps/SM
+            if (!strcmp(e, "28f")) return f.template run<2, 8, DIM3, 2, 2, 1, 1>();   // 2 lanes x 8 rows, 6-pair batches
+            if (!strcmp(e, "28f4")) return f.template run<2, 8, DIM3, 2, 0, 1, 1>();  // 2 lanes x 8 rows, 4-pair batches
+            if (!strcmp(e, "28g4")) return f.template run<2, 8, DIM3, 2, 0, 1, 2>();  // row-block-major slot order
         }
         if (const char *e = getenv("NNGP_TUNE_SHAPE"); e && m > 15 && m <= 31 && !f.sweep()) {
             if (!strcmp(e, "84")) return f.template run<8, 4, DIM3, 2, 0, 1, 0>();
