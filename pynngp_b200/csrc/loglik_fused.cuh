@@ -423,7 +423,9 @@ struct WarpSmem {
     static constexpr int pt_bytes = SOA3 ? 16 : int(sizeof(StagePt<T, DIM3>));
     static constexpr int stage_stride = P * pt_bytes + 16;
     // elements per location of the z array (SOA3) and of the elimination's column buffers: P entries, w_k, pad
-    static constexpr int col_stride = P + 2;
+    // (fp32, G = 4: 4-byte entries; a stride of P + 4 makes the eight 4-row windows of a warp tile the banks -- P + 2
+    // gave every store two wavefronts)
+    static constexpr int col_stride = P + ((sizeof(T) == 4 && G == 4) ? 4 : 2);
     static constexpr size_t zbuf = SOA3 ? size_t(sizeof(T) == 8 && G == 8 ? 6 : W) * col_stride * sizeof(T) : 0;
     // Where location g of the warp sits inside those arrays.  The kernel is bound by the shared-memory data stage
     // (profiles/r2a_fused_smem.txt), and with the W = 8 locations of a (4, R) shape in plain order the row-owner
@@ -438,7 +440,13 @@ struct WarpSmem {
     static constexpr bool PERM = sizeof(T) == 8 && G == 4, PERM8 = sizeof(T) == 8 && G == 8;
     static constexpr int col_slots = PERM8 ? 6 : W;
     __host__ __device__ static constexpr int col_pos(int g) { return PERM ? (g & 3) * 2 + (g >> 2) : PERM8 ? (g & 1) * 4 + (g >> 1) : g; }
-    __host__ __device__ static constexpr int stage_pos(int g) { return PERM ? (g & 1) * 4 + (g >> 1) : g; }
+    // fp32 with G = 4: its 2-D staged points are 8-byte entries at a 16-byte (mod 128) stride -- the case of the fp64
+    // column buffers -- and its 3-D ones 16-byte entries like the fp64 2-D points
+    static constexpr bool PERM32 = sizeof(T) == 4 && G == 4;
+    __host__ __device__ static constexpr int stage_pos(int g)
+    {
+        return (PERM || (PERM32 && DIM3)) ? (g & 1) * 4 + (g >> 1) : (PERM32 && !DIM3) ? (g & 3) * 2 + (g >> 2) : g;
+    }
     static constexpr size_t rec = size_t(W) * rec_stride;                 // gathered {x,y,z,yval} records
     static constexpr size_t e2 = DIM3 ? size_t(W) * P * sizeof(double) : 0;  // gathered eps2 (D = 3 only;
                                                                              // D < 3 records carry it in .z)
@@ -1283,8 +1291,8 @@ auto dispatch_shape(int m, const F &f)
         if (m <= 31) return f.template run<16, 2, DIM3, 2, 2, kElim, 1>();
         return f.template run<16, 3, DIM3, 2, 1>();
     } else {
-        if (m <= 7) return f.template run<4, 2, DIM3, 4, 0>();
-        if (m <= 15) return f.template run<4, 4, DIM3, 4, 0>();
+        if (m <= 7) return f.template run<4, 2, DIM3, 4, 0, kElim, 1>();
+        if (m <= 15) return f.template run<4, 4, DIM3, 4, 0, kElim, 1>();
         if (m <= 31) return f.template run<8, 4, DIM3, 4, 1>();
         return f.template run<16, 3, DIM3, 4, 1>();
     }
