@@ -7,7 +7,9 @@ import numpy as np
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from pynngp_b200 import _lib  # noqa: E402
+from pynngp_b200 import _lib, build as _build  # noqa: E402
+
+_lib.LIB_PATH = _build.TUNE_LIB  # the development library built with NNGP_DEV_DEFINES=NNGP_TIMELINE
 from pynngp_b200.synthetic import CONFIGS, PARAMS, synthetic  # noqa: E402
 
 c = dict(CONFIGS["cfg3"])
