@@ -15,6 +15,7 @@
 #include <string.h>
 
 #include <cmath>
+#include <mutex>
 #include <vector>
 
 #include "nngp_common.cuh"
@@ -53,12 +54,8 @@ int cuda_fail(nngp_handle *h, cudaError_t e, const char *what)
         if (e_ != cudaSuccess) return cuda_fail(h, e_, #call);             \
     } while (0)
 
-template <typename P>
-void free_dev(P *&p)
-{
-    if (p) cudaFree(p);
-    p = nullptr;
-}
+// every caller has its handle in `h`
+#define free_dev(p) free_dev_on(h, p)
 
 void family_shape(int dtype, int kernel_id, int m, int D, int *per_sm, int *lpw)
 {
@@ -103,32 +100,96 @@ int grid_for(nngp_handle *h, int kernel_id, int64_t nloc)
     return int(g);
 }
 
+// Parameter-independent part of the covariance build's exp table, one per device for the life of the process:
+// 2^(j/2048), j < 2048, followed by the table the unrolled kernels copy into shared memory as it is -- 2^(j/256),
+// j < 256, in 16 copies (copy c of entry j at [2048 + j * 16 + c]: one copy per lane of a half-warp, see
+// loglik_fused.cuh).  (Built per handle it was an allocation, a copy and a stream synchronisation in every nngp_create.)
+std::mutex g_tab_mu;
+double *g_exp2tab[64] = {};
+
+cudaError_t shared_exp2tab(int device, double **out)
+{
+    std::lock_guard<std::mutex> lk(g_tab_mu);
+    if (device < 0 || device >= 64) return cudaErrorInvalidDevice;
+    if (!g_exp2tab[device]) {
+        std::vector<double> tab(2048 + 4096);
+        for (int j = 0; j < 2048; ++j) tab[j] = exp2(double(j) / 2048.0);
+        for (int j = 0; j < 256; ++j)
+            for (int c = 0; c < 16; ++c) tab[2048 + j * 16 + c] = tab[j * 8];
+        double *d = nullptr;
+        cudaError_t e = cudaMalloc(&d, sizeof(double) * tab.size());
+        if (e == cudaSuccess) e = cudaMemcpy(d, tab.data(), sizeof(double) * tab.size(), cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) { if (d) cudaFree(d); return e; }
+        g_exp2tab[device] = d;
+    }
+    *out = g_exp2tab[device];
+    return cudaSuccess;
+}
+
+// Pinned host blocks of destroyed handles (parameter staging + the mapped result lines), kept for the next handle:
+// cudaMallocHost / cudaHostAlloc cost about a millisecond each, which is most of a new handle's first evaluation.
+struct HostBlock { double *stage; uint4 *out; int cap; };
+std::mutex g_host_mu;
+std::vector<HostBlock> g_host_free;
+
+void host_block_put(nngp_handle *h)
+{
+    if (!h->h_stage && !h->h_out) return;
+    std::lock_guard<std::mutex> lk(g_host_mu);
+    if (h->h_stage && h->h_out && g_host_free.size() < 64) g_host_free.push_back(HostBlock{h->h_stage, h->h_out, h->K_cap});
+    else {
+        if (h->h_stage) cudaFreeHost(h->h_stage);
+        if (h->h_out) cudaFreeHost(h->h_out);
+    }
+    h->h_stage = nullptr; h->h_out = nullptr;
+}
+
+cudaError_t host_block_get(nngp_handle *h, int cap)
+{
+    {
+        std::lock_guard<std::mutex> lk(g_host_mu);
+        int best = -1;
+        for (int k = 0; k < int(g_host_free.size()); ++k)
+            if (g_host_free[k].cap >= cap && (best < 0 || g_host_free[k].cap < g_host_free[best].cap)) best = k;
+        if (best >= 0) {
+            h->h_stage = g_host_free[best].stage; h->h_out = g_host_free[best].out;
+            g_host_free.erase(g_host_free.begin() + best);
+        }
+    }
+    if (!h->h_out) {
+        cudaError_t e = cudaMallocHost(&h->h_stage, sizeof(double) * NNGP_NPARAM * cap);
+        if (e == cudaSuccess) e = cudaHostAlloc(&h->h_out, sizeof(uint4) * NNGP_NSTAT * cap, cudaHostAllocMapped | cudaHostAllocPortable);
+        if (e != cudaSuccess) return e;
+    }
+    memset(h->h_out, 0, sizeof(uint4) * NNGP_NSTAT * cap);  // stamp 0 = never written (a handle's stamps start at 1)
+    return cudaSuccess;
+}
+
 // Evaluation scratch.  The ticket counters are zeroed on `st`, the stream the kernel is launched on: a
 // memset on another stream (the legacy NULL stream included) is not ordered against a non-blocking stream.
 int ensure_scratch(nngp_handle *h, int K, int grid, cudaStream_t st)
 {
     if (K > h->K_cap) {
-        CUDA_TRY(h, cudaStreamSynchronize(h->stream));  // nothing may still read the buffers being replaced
+        CUDA_TRY(h, quiesce(h));  // nothing may still read the buffers being replaced
         free_dev(h->d_params); free_dev(h->d_out); free_dev(h->d_counters);
-        if (h->h_stage) { cudaFreeHost(h->h_stage); h->h_stage = nullptr; }
-        if (h->h_out) { cudaFreeHost(h->h_out); h->h_out = nullptr; }
+        host_block_put(h);
         int cap = K < 16 ? 16 : K;
-        CUDA_TRY(h, cudaMalloc(&h->d_params, sizeof(double) * NNGP_NPARAM * cap));
-        CUDA_TRY(h, cudaMalloc(&h->d_out, sizeof(double) * NNGP_NSTAT * cap));
-        CUDA_TRY(h, cudaMalloc(&h->d_counters, sizeof(unsigned int) * cap));
+        CUDA_TRY(h, dev_malloc_on(h, &h->d_params, sizeof(double) * NNGP_NPARAM * cap));
+        CUDA_TRY(h, dev_malloc_on(h, &h->d_out, sizeof(double) * NNGP_NSTAT * cap));
+        CUDA_TRY(h, dev_malloc_on(h, &h->d_counters, sizeof(unsigned int) * cap));
+        if (st != h->stream) CUDA_TRY(h, cudaStreamSynchronize(h->stream));  // the blocks were allocated in h->stream's order
         CUDA_TRY(h, cudaMemsetAsync(h->d_counters, 0, sizeof(unsigned int) * cap, st));
-        CUDA_TRY(h, cudaMallocHost(&h->h_stage, sizeof(double) * NNGP_NPARAM * cap));
-        CUDA_TRY(h, cudaHostAlloc(&h->h_out, sizeof(uint4) * NNGP_NSTAT * cap, cudaHostAllocMapped | cudaHostAllocPortable));
-        memset(h->h_out, 0, sizeof(uint4) * NNGP_NSTAT * cap);  // stamp 0 = never written (stamps start at 1)
+        CUDA_TRY(h, host_block_get(h, cap));
         free_dev(h->d_partials);
         h->grid_cap = 0;
         h->K_cap = cap;
     }
     if (grid > h->grid_cap || !h->d_partials) {
-        CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+        CUDA_TRY(h, quiesce(h));
         free_dev(h->d_partials);
         int gc = grid < 1024 ? 1024 : grid;
-        CUDA_TRY(h, cudaMalloc(&h->d_partials, sizeof(double) * 3 * size_t(gc) * h->K_cap));
+        CUDA_TRY(h, dev_malloc_on(h, &h->d_partials, sizeof(double) * 3 * size_t(gc) * h->K_cap));
+        if (st != h->stream) CUDA_TRY(h, cudaStreamSynchronize(h->stream));
         h->grid_cap = gc;
     }
     return NNGP_OK;
@@ -292,35 +353,38 @@ int nngp_create(nngp_handle **out, int device, int dtype)
                     std::string("no CUDA device (this library has no CPU fallback): ") +
                         (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0"));
     if (device < 0 || device >= ndev) return fail(nullptr, NNGP_EINVAL, "device index out of range");
-    cudaDeviceProp prop;
-    if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) return cuda_fail(nullptr, e, "cudaGetDeviceProperties");
-    if (prop.major != 10)
+    // (single attributes: cudaGetDeviceProperties takes milliseconds)
+    int cc_major = 0, cc_minor = 0, num_sms = 0;
+    if ((e = cudaDeviceGetAttribute(&cc_major, cudaDevAttrComputeCapabilityMajor, device)) != cudaSuccess ||
+        (e = cudaDeviceGetAttribute(&cc_minor, cudaDevAttrComputeCapabilityMinor, device)) != cudaSuccess ||
+        (e = cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, device)) != cudaSuccess)
+        return cuda_fail(nullptr, e, "cudaDeviceGetAttribute");
+    if (cc_major != 10)
         return fail(nullptr, NNGP_ENODEVICE, "libnngp_b200 is built for sm_100a only; device is sm_" +
-                                                 std::to_string(prop.major) + std::to_string(prop.minor));
+                                                 std::to_string(cc_major) + std::to_string(cc_minor));
     if ((e = cudaSetDevice(device)) != cudaSuccess) return cuda_fail(nullptr, e, "cudaSetDevice");
     nngp_handle *h = new nngp_handle();
     h->device = device;
     h->dtype = dtype;
-    h->num_sms = prop.multiProcessorCount;
+    h->num_sms = num_sms;
     auto bail = [&](cudaError_t err, const char *what) {
         const int rc = cuda_fail(nullptr, err, what);
         nngp_destroy(h);
         return rc;
     };
     if ((e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "cudaStreamCreate");
-    if ((e = cudaMalloc(&h->d_tile_counter, sizeof(unsigned int))) != cudaSuccess) return bail(e, "cudaMalloc");
-    if ((e = cudaMalloc(&h->d_viol, sizeof(int32_t))) != cudaSuccess) return bail(e, "cudaMalloc");
-    {   // parameter-independent part of the covariance build's exp table: 2^(j/2048), j < 2048
-        // followed by the table the unrolled kernels copy into shared memory as it is: 2^(j/256), j < 256, in 16
-        // copies (copy c of entry j at [2048 + j * 16 + c]: one copy per lane of a half-warp, see loglik_fused.cuh)
-        std::vector<double> tab(2048 + 4096);
-        for (int j = 0; j < 2048; ++j) tab[j] = exp2(double(j) / 2048.0);
-        for (int j = 0; j < 256; ++j)
-            for (int c = 0; c < 16; ++c) tab[2048 + j * 16 + c] = tab[j * 8];
-        if ((e = cudaMalloc(&h->d_exp2tab, sizeof(double) * tab.size())) != cudaSuccess ||
-            (e = cudaMemcpy(h->d_exp2tab, tab.data(), sizeof(double) * tab.size(), cudaMemcpyHostToDevice)) != cudaSuccess)
-            return bail(e, "cudaMalloc");
+    {   // freed blocks stay in the device's pool (up to 8 GB) instead of going back to the driver at every synchronisation
+        cudaMemPool_t pool = nullptr;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess && pool) {
+            uint64_t keep = 8ull << 30, cur = 0;
+            if (cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &cur) == cudaSuccess && cur < keep)
+                cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+        cudaGetLastError();
     }
+    if ((e = dev_malloc_on(h, &h->d_tile_counter, sizeof(unsigned int))) != cudaSuccess) return bail(e, "cudaMalloc");
+    if ((e = dev_malloc_on(h, &h->d_viol, sizeof(int32_t))) != cudaSuccess) return bail(e, "cudaMalloc");
+    if ((e = shared_exp2tab(device, &h->d_exp2tab)) != cudaSuccess) return bail(e, "cudaMalloc (exp table)");
     *out = h;
     return NNGP_OK;
 }
@@ -411,16 +475,17 @@ void nngp_destroy(nngp_handle *h)
         return;
     }
     cudaSetDevice(h->device);
-    if (h->stream) cudaStreamSynchronize(h->stream);
+    if (h->stream) quiesce(h);
     free_dev(h->pts); free_dev(h->eps2); free_dev(h->nbr); free_dev(h->d_ystage);
     free_dev(h->d_params); free_dev(h->d_out); free_dev(h->d_partials);
-    free_dev(h->d_counters); free_dev(h->d_tile_counter); free_dev(h->d_exp2tab); free_dev(h->d_viol);
+    free_dev(h->d_counters); free_dev(h->d_tile_counter); free_dev(h->d_viol);
+    h->d_exp2tab = nullptr;  // the device's shared table (shared_exp2tab) outlives the handle
     for (void *&p : h->knn_scratch) free_dev(p);
     for (int r = 0; r < NNGP_MAX_PEERS; ++r)
         if (h->peer_base[r] && h->peer_base[r] != h->xbuf) cudaIpcCloseMemHandle(h->peer_base[r]);
-    free_dev(h->xbuf);
-    if (h->h_stage) cudaFreeHost(h->h_stage);
-    if (h->h_out) cudaFreeHost(h->h_out);
+    if (h->xbuf) cudaFree(h->xbuf);
+    h->xbuf = nullptr;
+    host_block_put(h);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -441,7 +506,7 @@ int nngp_set_data(nngp_handle *h, const double *coords, int64_t n, int D, const 
         return nngp_set_shard(h, 0, n);
     }
     CUDA_TRY(h, cudaSetDevice(h->device));
-    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    CUDA_TRY(h, quiesce(h));
     free_dev(h->pts); free_dev(h->eps2); free_dev(h->nbr); free_dev(h->d_ystage);  // the landing buffer is sized by n
     h->has_nbr = false; h->m = 0; h->nbr_row0 = 0; h->nbr_rows = 0;
     h->n = n; h->D = D; h->lo = 0; h->hi = n;
@@ -454,13 +519,13 @@ int nngp_set_data(nngp_handle *h, const double *coords, int64_t n, int D, const 
         cudaError_t e_ = (call);                                               \
         if (e_ != cudaSuccess) { cleanup(); free_dev(h->eps2); free_dev(h->pts); return cuda_fail(h, e_, #call); }  \
     } while (0)
-    SET_TRY(cudaMalloc(&h->pts, sizeof(double4) * (size_t)n));
-    SET_TRY(cudaMalloc(&d_coords, sizeof(double) * (size_t)n * D));
-    SET_TRY(cudaMalloc(&d_y, sizeof(double) * (size_t)n));
+    SET_TRY(dev_malloc_on(h, &h->pts, sizeof(double4) * (size_t)n));
+    SET_TRY(dev_malloc_on(h, &d_coords, sizeof(double) * (size_t)n * D));
+    SET_TRY(dev_malloc_on(h, &d_y, sizeof(double) * (size_t)n));
     SET_TRY(cudaMemcpyAsync(d_coords, coords, sizeof(double) * (size_t)n * D, cudaMemcpyHostToDevice, h->stream));
     SET_TRY(cudaMemcpyAsync(d_y, y, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, h->stream));
     if (eps2) {
-        SET_TRY(cudaMalloc(&d_e2, sizeof(double) * (size_t)n));
+        SET_TRY(dev_malloc_on(h, &d_e2, sizeof(double) * (size_t)n));
         SET_TRY(cudaMemcpyAsync(d_e2, eps2, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, h->stream));
         if (D > 2) h->eps2 = d_e2;  // D = 3: kept as its own array; D < 3: folded into the records' z slot
     }
@@ -481,7 +546,7 @@ int nngp_set_y(nngp_handle *h, const double *y)
     if (!y) return fail(h, NNGP_EINVAL, "y must not be NULL");
     CUDA_TRY(h, cudaSetDevice(h->device));
     // one contiguous copy, then a kernel writes the yval lane of the records (pack.cu)
-    if (!h->d_ystage) CUDA_TRY(h, cudaMalloc(&h->d_ystage, sizeof(double) * (size_t)h->n));
+    if (!h->d_ystage) CUDA_TRY(h, dev_malloc_on(h, &h->d_ystage, sizeof(double) * (size_t)h->n));
     CUDA_TRY(h, cudaMemcpyAsync(h->d_ystage, y, sizeof(double) * (size_t)h->n, cudaMemcpyHostToDevice, h->stream));
     CUDA_TRY(h, launch_scatter_lane(h, h->d_ystage, 3, h->stream));
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
@@ -499,10 +564,10 @@ int nngp_set_eps2(nngp_handle *h, const double *eps2)
     if (!eps2) return fail(h, NNGP_EINVAL, "eps2 must not be NULL");
     CUDA_TRY(h, cudaSetDevice(h->device));
     if (h->D > 2) {  // D = 3: its own array (the records' z slot holds a coordinate)
-        if (!h->eps2) CUDA_TRY(h, cudaMalloc(&h->eps2, sizeof(double) * (size_t)h->n));
+        if (!h->eps2) CUDA_TRY(h, dev_malloc_on(h, &h->eps2, sizeof(double) * (size_t)h->n));
         CUDA_TRY(h, cudaMemcpyAsync(h->eps2, eps2, sizeof(double) * (size_t)h->n, cudaMemcpyHostToDevice, h->stream));
     } else {         // D < 3: the records' z slot
-        if (!h->d_ystage) CUDA_TRY(h, cudaMalloc(&h->d_ystage, sizeof(double) * (size_t)h->n));
+        if (!h->d_ystage) CUDA_TRY(h, dev_malloc_on(h, &h->d_ystage, sizeof(double) * (size_t)h->n));
         CUDA_TRY(h, cudaMemcpyAsync(h->d_ystage, eps2, sizeof(double) * (size_t)h->n, cudaMemcpyHostToDevice, h->stream));
         CUDA_TRY(h, launch_scatter_lane(h, h->d_ystage, 2, h->stream));
     }
@@ -538,10 +603,10 @@ static int alloc_nbr(nngp_handle *h, int m, int64_t row0, int64_t rows)
 {
     if (m < 1 || m > NNGP_MAX_M) return fail(h, NNGP_EINVAL, "m must be in [1, 32]");
     if (h->nbr && (h->m != m || h->nbr_rows != rows)) {
-        CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+        CUDA_TRY(h, quiesce(h));
         free_dev(h->nbr);
     }
-    if (!h->nbr) CUDA_TRY(h, cudaMalloc(&h->nbr, sizeof(int32_t) * (size_t)(rows > 0 ? rows : 1) * m));
+    if (!h->nbr) CUDA_TRY(h, dev_malloc_on(h, &h->nbr, sizeof(int32_t) * (size_t)(rows > 0 ? rows : 1) * m));
     h->m = m; h->nbr_row0 = row0; h->nbr_rows = rows;
     h->has_nbr = false;
     return NNGP_OK;
@@ -736,13 +801,13 @@ int nngp_knn_plain(nngp_handle *h, int k, int32_t *out)
     if (!out || k < 1 || k > NNGP_MAX_M) return fail(h, NNGP_EINVAL, "need out != NULL and 1 <= k <= 32");
     CUDA_TRY(h, cudaSetDevice(h->device));
     int32_t *d_tab = nullptr;
-    CUDA_TRY(h, cudaMalloc(&d_tab, sizeof(int32_t) * (size_t)h->n * k));
+    CUDA_TRY(h, dev_malloc_on(h, &d_tab, sizeof(int32_t) * (size_t)h->n * k));
     int used = 0;
     cudaError_t e = launch_knn_grid(h, false, k, 0, h->n, INT64_MAX, d_tab, false, h->stream, 0, &used);
     if (e == cudaSuccess && !used) e = launch_knn_plain(h, k, d_tab, h->stream);
     if (e == cudaSuccess) e = cudaMemcpyAsync(out, d_tab, sizeof(int32_t) * (size_t)h->n * k, cudaMemcpyDeviceToHost, h->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
-    cudaFree(d_tab);
+    free_dev(d_tab);
     if (e != cudaSuccess) return cuda_fail(h, e, "nngp_knn_plain");
     return NNGP_OK;
 }
@@ -762,6 +827,7 @@ int nngp_loglik_device(nngp_handle *h, int kernel_id, const double *d_params, in
     if (!d_out) return fail(h, NNGP_EINVAL, "d_out must not be NULL");
     CUDA_TRY(h, cudaSetDevice(h->device));
     cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+    if (st != h->stream) h->foreign_stream_used = true;
     return launch_eval(h, kernel_id, d_params, nullptr, K, d_out, nullptr, 0, nullptr, st);
 }
 
@@ -776,7 +842,8 @@ int nngp_peer_export(nngp_handle *h, int K_cap, unsigned char *handle_out)
     if (K_cap > h->num_sms) return fail(h, NNGP_EINVAL, "K_cap must not exceed the number of SMs");
     if (h->px.world > 1) return fail(h, NNGP_ESTATE, "peer exchange is already connected");
     CUDA_TRY(h, cudaSetDevice(h->device));
-    free_dev(h->xbuf);
+    if (h->xbuf) cudaFree(h->xbuf);
+    h->xbuf = nullptr;
     CUDA_TRY(h, cudaMalloc(&h->xbuf, peer_bytes(K_cap)));
     CUDA_TRY(h, cudaMemset(h->xbuf, 0, peer_bytes(K_cap)));
     CUDA_TRY(h, cudaDeviceSynchronize());
@@ -827,6 +894,7 @@ int nngp_loglik_device_allreduce(nngp_handle *h, int kernel_id, const double *d_
     if (K > h->px.K_cap) return fail(h, NNGP_EINVAL, "K exceeds the exchange buffer's K_cap");
     CUDA_TRY(h, cudaSetDevice(h->device));
     cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+    if (st != h->stream) h->foreign_stream_used = true;
     PeerExchange px = h->px;
     px.gen = h->px.gen + 1;  // every rank issues the same sequence of exchanges
     if ((rc = launch_eval(h, kernel_id, d_params, nullptr, K, d_out, nullptr, 0, &px, st))) return rc;
@@ -935,11 +1003,11 @@ static int run_emit(nngp_handle *h, int kernel_id, const double *params, int64_t
         cudaError_t e_ = (call);                                               \
         if (e_ != cudaSuccess) { cleanup(); return cuda_fail(h, e_, #call); }  \
     } while (0)
-    if (B) EMIT_TRY(cudaMalloc(&dB, sizeof(double) * cap * m));
-    if (F) EMIT_TRY(cudaMalloc(&dF, sizeof(double) * cap));
-    if (CN) EMIT_TRY(cudaMalloc(&dCN, sizeof(double) * cap * m * m));
-    if (cc) EMIT_TRY(cudaMalloc(&dcc, sizeof(double) * cap * m));
-    if (cs) EMIT_TRY(cudaMalloc(&dcs, sizeof(double) * cap));
+    if (B) EMIT_TRY(dev_malloc_on(h, &dB, sizeof(double) * cap * m));
+    if (F) EMIT_TRY(dev_malloc_on(h, &dF, sizeof(double) * cap));
+    if (CN) EMIT_TRY(dev_malloc_on(h, &dCN, sizeof(double) * cap * m * m));
+    if (cc) EMIT_TRY(dev_malloc_on(h, &dcc, sizeof(double) * cap * m));
+    if (cs) EMIT_TRY(dev_malloc_on(h, &dcs, sizeof(double) * cap));
     if ((rc = ensure_scratch(h, 1, grid_for(h, kernel_id, cap), h->stream))) { cleanup(); return rc; }
     for (int64_t s0 = i0; s0 < i1; s0 += cap) {
         const int64_t s1 = s0 + cap < i1 ? s0 + cap : i1;

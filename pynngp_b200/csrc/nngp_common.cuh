@@ -67,7 +67,7 @@ struct nngp_handle {
     double *d_partials = nullptr;  // K_cap x grid_cap x 3
     unsigned int *d_counters = nullptr;  // K_cap tickets for the last-block reduction
     unsigned int *d_tile_counter = nullptr;
-    double *d_exp2tab = nullptr;   // 2^(j/2048), j < 2048, then 16 copies of 2^(j/256), j < 256 (built once at nngp_create)
+    double *d_exp2tab = nullptr;   // 2^(j/2048), j < 2048, then 16 copies of 2^(j/256), j < 256 (the device's shared table, not owned)
     double *h_stage = nullptr;     // pinned: K_cap x 4 parameter staging (K > NNGP_PV_MAX only)
     // results of the host-pointer calls land in MAPPED pinned host memory, written by the kernel's last
     // block itself, followed by a sequence stamp per blockIdx.y the host polls: no D2H copy, no stream sync
@@ -86,6 +86,10 @@ struct nngp_handle {
 
     int shape_key = -1, shape_per_sm = 1, shape_lpw = 8;  // cached occupancy of the fused kernel in use
 
+    // a *_device entry point ran on a caller's stream: before a buffer goes back to the pool the whole device is
+    // synchronised (what cudaFree did implicitly), not just the handle's stream
+    bool foreign_stream_used = false;
+
     int64_t launches = 0;
     std::string err;
     // optional device-side timing of the evaluation launches (nngp_set_timing): events around the kernel
@@ -95,6 +99,33 @@ struct nngp_handle {
     // multi-device handle (nngp_create_multi): one sub-handle per device, driven by worker threads
     struct nngp_group *group = nullptr;
 };
+
+// Device memory of a handle comes from the device's stream-ordered pool (cudaMallocAsync / cudaFreeAsync on the
+// handle's stream, release threshold raised at nngp_create): a freed block goes back to the pool, not to the driver,
+// so rebuilding a model -- or the next handle -- reuses it without a cudaMalloc / cudaFree round trip (those cost
+// 0.1-1 ms each and cudaFree synchronises the device: 3 ms of a 5.5 ms constructor at n = 1e5, and up to 25 ms when
+// large blocks were released just before).  The exchange buffers stay on cudaMalloc (CUDA IPC and peer access are
+// not defined for pool memory by default).
+template <typename P>
+inline cudaError_t dev_malloc_on(nngp_handle *h, P **p, size_t bytes)
+{
+    return cudaMallocAsync(reinterpret_cast<void **>(p), bytes ? bytes : 1, h->stream);
+}
+// nothing of the handle's may still be in flight (call before buffers are released or replaced)
+inline cudaError_t quiesce(nngp_handle *h)
+{
+    if (h->foreign_stream_used) {
+        h->foreign_stream_used = false;
+        return cudaDeviceSynchronize();
+    }
+    return h->stream ? cudaStreamSynchronize(h->stream) : cudaSuccess;
+}
+template <typename P>
+inline void free_dev_on(nngp_handle *h, P *&p)
+{
+    if (p) cudaFreeAsync(p, h->stream);
+    p = nullptr;
+}
 
 // Arguments of the fused covariance + factorisation + reduction kernel.
 constexpr int NNGP_PV_MAX = 8;  // parameter vectors that travel in the kernel arguments (no H2D copy)

@@ -100,11 +100,11 @@ cudaError_t launch_validate_table(nngp_handle *h, const int32_t *rows, int m, in
 cudaError_t scratch_get(nngp_handle *h, int slot, size_t bytes, void **p)
 {
     if (h->knn_scratch_bytes[slot] < bytes) {
-        if (h->knn_scratch[slot]) cudaFree(h->knn_scratch[slot]);
+        free_dev_on(h, h->knn_scratch[slot]);
         h->knn_scratch[slot] = nullptr;
         h->knn_scratch_bytes[slot] = 0;
         const size_t want = bytes + bytes / 8;  // a little headroom: the next build is often slightly larger
-        cudaError_t e = cudaMalloc(&h->knn_scratch[slot], want);
+        cudaError_t e = dev_malloc_on(h, &h->knn_scratch[slot], want);
         if (e != cudaSuccess) return e;
         h->knn_scratch_bytes[slot] = want;
     }
@@ -132,7 +132,7 @@ cudaError_t launch_pack_records(nngp_handle *h, const double *d_coords, const do
     int grid = int(std::min<int64_t>((n + kBlock - 1) / kBlock, int64_t(h->num_sms) * 4));
     if (grid < 1) grid = 1;
     double *d_part = nullptr;
-    cudaError_t e = cudaMalloc(&d_part, sizeof(double) * 7 * size_t(grid));
+    cudaError_t e = dev_malloc_on(h, &d_part, sizeof(double) * 7 * size_t(grid));
     if (e != cudaSuccess) return e;
     pack_records_kernel<<<grid, kBlock, 0, stream>>>(d_coords, d_y, d_eps2, n, h->D, h->pts, d_part);
     ++h->launches;
@@ -140,7 +140,7 @@ cudaError_t launch_pack_records(nngp_handle *h, const double *d_coords, const do
     if ((e = cudaGetLastError()) == cudaSuccess)
         e = cudaMemcpyAsync(part.data(), d_part, sizeof(double) * part.size(), cudaMemcpyDeviceToHost, stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
-    cudaFree(d_part);
+    free_dev_on(h, d_part);
     if (e != cudaSuccess) return e;
     double lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY}, bad = 0.0;
     for (int b = 0; b < grid; ++b) {
