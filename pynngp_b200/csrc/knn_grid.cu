@@ -83,16 +83,26 @@ __global__ void __launch_bounds__(1024) scan_cells_kernel(const int *counts, int
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     int running = 0;
     double sq = 0.0;
-    constexpr int IPT = 16;  // cells per thread and round: a round costs three block barriers whatever it scans
+    constexpr int IPT = 4;  // cells per thread and round (consecutive lanes read consecutive 16-byte groups; 16 per thread made the
+                            // accesses 64-byte strided and the kernel 1.6x slower)
+    // the next round's counts are loaded before this round's barriers (a round is otherwise one L2 round trip long)
+    int vnext[IPT];
+#pragma unroll
+    for (int k = 0; k < IPT; ++k) vnext[k] = tid * IPT + k < ncell ? in[tid * IPT + k] : 0;
     for (int base = 0; base < ncell; base += 1024 * IPT) {
         const int k0 = base + tid * IPT;
         int v[IPT];
         int s = 0;
 #pragma unroll
         for (int k = 0; k < IPT; ++k) {
-            v[k] = k0 + k < ncell ? in[k0 + k] : 0;
+            v[k] = vnext[k];
             sq += double(v[k]) * double(v[k]);
             s += v[k];
+        }
+#pragma unroll
+        for (int k = 0; k < IPT; ++k) {
+            const int kn = k0 + 1024 * IPT + k;
+            vnext[k] = kn < ncell ? in[kn] : 0;
         }
         int incl = s;
 #pragma unroll
