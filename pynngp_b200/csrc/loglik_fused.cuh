@@ -10,16 +10,18 @@
 //     identity padding, row P-1 = the location itself,
 // with the right-hand side w = [y_N(i); 0; y_i].  An LDL^T elimination of M gives, at the last
 // pivot, D_{P-1} = F_i and the eliminated w_{P-1} = r_i = y_i - b_i^T y_N(i): the log-likelihood
-// needs no back-substitution.  G lanes share one location (P = G*R rows, lane q owns rows
-// q, q+G, ..., kept in registers); a warp carries 32/G locations.  Pivot column entries travel by
-// width-G warp shuffles, everything else is lane-local FP64 (or FP32) arithmetic.  Neighbour
-// coordinates are gathered once per location as 32-byte records and staged in shared memory for
-// the column reads of the covariance build.  Block partials are written per block and summed in a
-// fixed order by the last block to finish (deterministic for a given grid).
+// needs no back-substitution.  G lanes share one location (P = G*R rows, each lane owning R of them -- folded, see
+// row_of -- kept in registers); a warp carries 32/G locations.  Pivot columns travel through two alternating
+// shared-memory buffers (one __syncwarp per pivot), everything else is lane-local FP64 (or FP32) arithmetic.
+// Neighbour coordinates are gathered once per location as 32-byte records (cp.async, one iteration ahead) and
+// staged in shared memory for the column reads of the covariance build.  Block partials are written per block and
+// summed in a fixed order by the last block to finish (deterministic for a given grid).
 //
-// Bound: the FP64 (FP32) vector pipe -- each pair costs a sqrt and an exp; HBM traffic is the
-// 4m+32 B/location of compulsory reads.  Tensor cores do not apply: per-location work is
-// a 16x16 / 32x32 factorisation with a serial pivot chain plus transcendental covariance entries.
+// Bound (ncu): the unit closest to its peak is the shared-memory DATA STAGE (one 128-byte wavefront
+// per cycle per SM; 84 % before round 2's layout work, 73 % after), then the FP64 pipe (51 %) and the issue slots
+// (51 %); HBM traffic is the 4m+32 B/location of compulsory reads (3 % of peak).  Every shared-memory access here is
+// laid out for its minimum wavefront count (WarpSmem).  Tensor cores do not apply: per-location work is a 16x16 /
+// 32x32 factorisation with a serial pivot chain plus transcendental covariance entries.
 #pragma once
 #include <math.h>
 #include <stdlib.h>
@@ -140,8 +142,8 @@ __device__ __forceinline__ float fast_rcp(float x)
 }
 
 // sigma2 * exp(-u) for u >= 0.  fp64: table of sigma2 * 2^(j/2^TB) in shared memory (tab) + a short
-// polynomial -> 7 (TB = 11) to 9 (TB = 6) FP64 instructions.  u >= 708 (which includes the far-away
-// sentinel rows) returns exactly 0.
+// polynomial -> 8 (TB = 8) to 9 (TB = 6) FP64 instructions.  u >= 708 (which includes the far-away
+// sentinel rows) returns exactly 0 (this single-value form; the batch form caps u at 700 instead, see corr_batch).
 template <int TB, int REP = 0>
 __device__ __forceinline__ double scaled_exp_neg(double u, const double *tab, double /*sigma2*/)
 {
