@@ -743,6 +743,33 @@ def test_host_result_path_stress():
             assert e.loglik_terms(1, *prm[0, :3]) == one
 
 
+def test_handles_reuse_pooled_memory():
+    """Handles come and go with different sizes and shapes: device blocks, pinned result lines and the exp table are
+    recycled between them (stream-ordered pool, per-process caches), so nothing may depend on fresh, zeroed memory."""
+    rng = np.random.default_rng(5)
+    for it in range(14):
+        n = int(rng.integers(300, 6000))
+        D = int(rng.integers(1, 4))
+        m = int(rng.choice([3, 7, 10, 15, 30]))
+        kid = int(rng.integers(0, 3))
+        s, y = synthetic(n, D, 100 + it)
+        e = engine(s, y, dtype="float64" if it % 3 else "float32")
+        e.build_neighbors_grid(m)
+        tab = e.get_neighbors()
+        assert np.array_equal(tab, orc.c_knn_ordered(s, m)), (it, n, D, m)
+        prm = np.array([[1.1, 5.0 + it, 0.05, 0.0], [0.9, 8.0, 0.2, 0.0]])
+        got = e.loglik(kid, prm[: 1 + it % 2])
+        for k in range(1 + it % 2):
+            want = orc.c_loglik(s, y, tab, kid, *prm[k, :3])
+            np.testing.assert_allclose(got[k][:2], want[:2], rtol=RTOL64 if it % 3 else 1e-3)  # (this test hunts stale memory, not fp32 precision)
+            assert got[k][2] == want[2]
+        if it % 4 == 0:
+            e.set_data(s[: n // 2], y[: n // 2])  # the same handle again, smaller
+            e.build_neighbors_grid(m)
+            assert np.array_equal(e.get_neighbors(), tab[: n // 2])
+        e.close()
+
+
 def _need_gpus(k):
     if _lib.device_count() < k:
         pytest.skip(f"needs {k} GPUs")
