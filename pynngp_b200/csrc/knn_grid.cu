@@ -174,18 +174,19 @@ __global__ void scatter_kernel(const double4 *__restrict__ pts, int N, int ncand
 // then inserted by the whole sub-warp: its (d2, j) is broadcast from the lane that holds it, every list lane
 // compares its own entry against it, the population count of that ballot is the insertion position, and the tail
 // of the list moves up one lane with __shfl_up_sync (the old m-th best falls off the end).  Nothing is kept in
-// shared memory and no lane loops over the list.  d2 >= +0 always, so (d2, j) is compared on the bit patterns --
-// unsigned 64-bit order equals numeric order for non-negative doubles -- which keeps the FP64 pipe for distances.
+// shared memory and no lane loops over the list.  (d2, j) is compared with FP64 set-predicate instructions: the kernel
+// is bound by its issue slots (80 % active, FP64 pipe 3 %), and a 64-bit integer compare costs two to three more
+// instructions than a DSETP.
 // The threshold the ballot uses is refreshed once per SW candidates, not per insertion: a stale threshold only
 // lets a few candidates through that land beyond position m - 1, where they are dropped.
 constexpr int QTHREADS = 256;  // threads per block of the query kernel
 constexpr int32_t kNoId = 0x7fffffff;
 
 struct Cand {
-    unsigned long long key;  // bit pattern of d2 (>= +0)
+    double key;  // d2 (never NaN: the coordinates are finite)
     int32_t id;
 };
-__device__ __forceinline__ bool cand_less(unsigned long long ka, int32_t ia, unsigned long long kb, int32_t ib)
+__device__ __forceinline__ bool cand_less(double ka, int32_t ia, double kb, int32_t ib)
 {
     return ka < kb || (ka == kb && ia < ib);
 }
@@ -202,7 +203,7 @@ __global__ void __launch_bounds__(QTHREADS) knn_grid_query_kernel(const double4 
 {
     constexpr unsigned FULL = 0xffffffffu;
     constexpr unsigned SUBMASK = 0xffffffffu >> (32 - SW);
-    constexpr unsigned long long kInf = 0x7ff0000000000000ull;
+    const double kInf = INFINITY;
     const int lane = threadIdx.x & 31;
     const int sl = lane % SW;             // lane inside the sub-warp = list position it holds
     const int sshift = lane - sl;         // first lane of the sub-warp
@@ -220,9 +221,9 @@ __global__ void __launch_bounds__(QTHREADS) knn_grid_query_kernel(const double4 
     c /= Gx;
     const int cy = c % Gy, cz = c / Gy;
 
-    unsigned long long key = kInf;  // this lane's list entry
+    double key = kInf;  // this lane's list entry
     int32_t id = kNoId;
-    unsigned long long worst = kInf;  // the sub-warp's m-th best (the acceptance threshold), refreshed per batch
+    double worst = kInf;  // the sub-warp's m-th best (the acceptance threshold), refreshed after a batch that inserted
     int32_t worst_id = kNoId;
 
     const double2 *rec = reinterpret_cast<const double2 *>(sorted);
@@ -242,19 +243,20 @@ __global__ void __launch_bounds__(QTHREADS) knn_grid_query_kernel(const double4 
                     const double dz = qz - b.x;
                     d = __dadd_rn(d, __dmul_rn(dz, dz));
                 }
-                cd.key = (unsigned long long)__double_as_longlong(d);
+                cd.key = d;
                 pass = (!ORDERED || cd.id < jlim) && cand_less(cd.key, cd.id, worst, worst_id);
             }
             unsigned todo = (__ballot_sync(FULL, pass) >> sshift) & SUBMASK;  // this sub-warp's survivors
+            if (!__any_sync(FULL, todo != 0)) continue;  // nothing to insert anywhere in the warp: the thresholds stand
             while (__any_sync(FULL, todo != 0)) {
                 const bool act = todo != 0;
                 const int src = act ? __ffs(todo) - 1 : 0;
-                const unsigned long long ck = __shfl_sync(FULL, cd.key, src, SW);
+                const double ck = __shfl_sync(FULL, cd.key, src, SW);
                 const int32_t cj = __shfl_sync(FULL, cd.id, src, SW);
                 // list entries that sort before the candidate form a prefix: its length is the position
                 const bool before = sl < m && cand_less(key, id, ck, cj);
                 const int pos = __popc((__ballot_sync(FULL, before) >> sshift) & SUBMASK);
-                const unsigned long long kup = __shfl_up_sync(FULL, key, 1, SW);
+                const double kup = __shfl_up_sync(FULL, key, 1, SW);
                 const int32_t iup = __shfl_up_sync(FULL, id, 1, SW);
                 if (act) {
                     if (sl == pos) { key = ck; id = cj; }
@@ -308,7 +310,7 @@ __global__ void __launch_bounds__(QTHREADS) knn_grid_query_kernel(const double4 
                 if (cz - r > 0) bound = fmin(bound, qz - (gs.lo[2] + double(cz - r) * gs.h[2]));
                 if (cz + r < Gz - 1) bound = fmin(bound, (gs.lo[2] + double(cz + r + 1) * gs.h[2]) - qz);
                 const double bs = bound * (1.0 - 1e-9) - gs.slack;
-                if (bs > 0.0 && __longlong_as_double((long long)worst) < bs * bs) done = true;
+                if (bs > 0.0 && worst < bs * bs) done = true;
             }
         }
     }
