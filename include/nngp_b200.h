@@ -25,6 +25,11 @@
  *     *_device calls take device pointers and a cudaStream_t (as void*), are asynchronous, and are
  *     what an on-device sweep/MCMC loop uses.
  *   - a handle is not thread-safe; distinct handles are independent.
+ *   - device memory comes from the device's default stream-ordered pool (cudaMallocAsync on the handle's stream; the
+ *     pool's release threshold is raised to 8 GB at nngp_create), so the blocks of a destroyed handle -- and the
+ *     pinned result lines, and the per-device exp table -- serve the next one: a model can be rebuilt without paying
+ *     for cudaMalloc / cudaFree again.  If a *_device entry point ran on a caller's stream, the next call that
+ *     releases or replaces buffers synchronises the whole device first.
  *   - there is NO CPU fallback: without a CUDA device nngp_create fails with NNGP_ENODEVICE.
  */
 #ifndef NNGP_B200_H
