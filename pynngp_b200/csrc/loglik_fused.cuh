@@ -708,12 +708,29 @@ __global__ void __launch_bounds__(kThreads, MINB) fused_loglik_kernel(const __gr
             const double sx = self0.x, sy = self0.y;
             const double sz = DIM3 ? recs[2 * (P - 1) + 1].x : 0.0;
             const double diag0 = SWEEP ? 1.0 : s_diag[0], inv_s2 = SWEEP ? 1.0 : s_diag[1];  // sweep: set per vector below
+            bool mine = true;
+#pragma unroll
+            for (int s = 0; s < R; ++s) mine &= nidx[s] >= 0;
+            const bool all_valid = __all_sync(0xffffffffu, mine);  // warp-uniform
 #pragma unroll
             for (int s = 0; s < R; ++s) {
                 const int r = rowq(s);
                 valid[s] = nidx[s] >= 0;
                 double2 v0 = make_double2(0.0, 0.0), v1 = make_double2(0.0, 0.0);
                 double e2 = 0.0;
+                if (all_valid) {
+                    // every row of every location of the warp exists (any group past the first few rows of the ordering
+                    // when m = P - 1): no padding, so no selects
+                    v0 = recs[2 * r];
+                    v1 = recs[2 * r + 1];
+                    if (!DIM3) e2 = v1.x;
+                    else if (a.eps2) e2 = e2buf[g * P + r];
+                    rx[s] = T((v0.x - sx) * phi);
+                    ry[s] = T((v0.y - sy) * phi);
+                    rz[s] = T((v1.x - sz) * phi);
+                    w[s] = T(v1.y);
+                    dg[s] = T(FACT && !SWEEP ? fma(e2, inv_s2, diag0) : diag0 + e2);
+                } else {
                 if (valid[s]) {
                     v0 = recs[2 * r];
                     v1 = recs[2 * r + 1];
@@ -726,6 +743,7 @@ __global__ void __launch_bounds__(kThreads, MINB) fused_loglik_kernel(const __gr
                 rz[s] = valid[s] ? T((v1.x - sz) * phi) : T(0);
                 w[s] = valid[s] ? T(v1.y) : T(0);
                 dg[s] = valid[s] ? T(FACT && !SWEEP ? fma(e2, inv_s2, diag0) : diag0 + e2) : T(1);
+                }
                 w0[s] = w[s];
                 e2r[s] = T(e2);
                 Pt pt;
