@@ -341,6 +341,15 @@ def run_ours(args, cfg):
             out["stream"], out["d_bufs"] = stream, (d_prm, d_out)
         return out
 
+    # the library's kernels are loaded lazily at their first launch: a 2000-row model pays that once, untimed, so that
+    # setup_s / knn_build_s below are the workload's own
+    ws_, wy_ = synthetic(2000, cfg["D"], 99)
+    for dev_ in (range(ngpu) if single_process else (local,)):
+        we_ = _lib.Engine(dev_, args.dtype)
+        we_.set_data(ws_, wy_)
+        we_.build_neighbors_grid(cfg["m"])
+        we_.loglik(KIDS[cfg["kernel"]], np.array([PARAMS["sigma2"], PARAMS["phi"], PARAMS["tau2"], 0.0]))
+        we_.close()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
