@@ -22,9 +22,9 @@ timeout 300 python tools/knn_bench.py cfg4 --lams 0.5,1,2,4 > gpurun_out/${TAG}_
 if [ "$2" != "noncu" ]; then
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:fused_loglik -c 2 -f -o gpurun_out/${TAG}_prof_fused \
     python tools/prof_driver.py cfg3 float64 2 > gpurun_out/${TAG}_ncu_fused.log 2>&1; echo "ncu fused rc=$?"
-true || timeout 600 ncu --set full --clock-control none --import-source on -k regex:fused_loglik -c 1 -f -o gpurun_out/${TAG}_prof_fused_m30 \
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:fused_loglik -c 1 -f -o gpurun_out/${TAG}_prof_fused_m30 \
     python tools/prof_driver.py cfg4 float64 1 2000000 > gpurun_out/${TAG}_ncu_fused_m30.log 2>&1; echo "ncu fused m30 rc=$?"
-true || timeout 600 ncu --set full --clock-control none --import-source on -k regex:knn_grid_query -c 3 -f -o gpurun_out/${TAG}_prof_knn \
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:knn_grid_query -c 3 -f -o gpurun_out/${TAG}_prof_knn \
     python tools/prof_driver.py cfg3 float64 1 > gpurun_out/${TAG}_ncu_knn.log 2>&1; echo "ncu knn rc=$?"
 fi
 ls gpurun_out | grep ${TAG} | head -30
