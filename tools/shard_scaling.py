@@ -7,7 +7,10 @@ import numpy as np
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from pynngp_b200 import _lib  # noqa: E402
+from pynngp_b200 import _lib, build as _build  # noqa: E402
+
+if os.environ.get("NNGP_USE_DEV_LIB"):  # A/B against the development library (python -m pynngp_b200.build --tune)
+    _lib.LIB_PATH = _build.TUNE_LIB
 from pynngp_b200.synthetic import CONFIGS, PARAMS, synthetic  # noqa: E402
 
 c = dict(CONFIGS[sys.argv[1] if len(sys.argv) > 1 else "cfg3"])
